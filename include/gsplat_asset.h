@@ -1,0 +1,70 @@
+/* gsplat_asset.h -- C ABI of the host-side asset packer and synthetic-scene generator.
+ *
+ * Host (CPU) code, no CUDA.  It reproduces the byte layout written by the reference's
+ * importer (package/Editor/GaussianSplatAssetCreator.cs) so that
+ * synthetic scenes enter the render path in exactly the format a Unity-made
+ * GaussianSplatAsset would.  Citations: E/ = package/Editor, R/ = package/Runtime.
+ */
+#ifndef GSPLAT_ASSET_H
+#define GSPLAT_ASSET_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSA_API __attribute__((visibility("default")))
+
+/* E/Utils/GaussianFileReader.cs:17-26 -- 62 floats / 248 bytes, AFTER LinearizeData
+ * (:210-232): rot = PackSmallest3Rotation output (xyz in 0..1, w = index/3),
+ * scale linear, dc0 = colour, opacity = sigmoid. */
+typedef struct GsaInputSplat {
+  float pos[3];
+  float nor[3];
+  float dc0[3];
+  float sh[45]; /* sh1..shF, each rgb */
+  float opacity;
+  float scale[3];
+  float rot[4];
+} GsaInputSplat;
+
+typedef struct GsaSizes {
+  uint64_t pos_bytes, other_bytes, color_bytes, sh_bytes, chunk_bytes;
+  uint32_t tex_width, tex_height;
+} GsaSizes;
+
+enum GsaSceneKind {
+  GSA_SCENE_LATTICE = 0,   /* BASELINE cfg1: axis-aligned lattice with deliberate depth ties */
+  GSA_SCENE_CLUSTERED = 1, /* cfg2-4 "scene-like": clusters + background shell */
+  GSA_SCENE_UNIFORM = 2    /* cfg5 "random gaussians" */
+};
+
+/* Deterministic synthetic splats.  Writes n GsaInputSplat records. */
+GSA_API int gsa_generate(uint32_t kind, uint32_t n, uint32_t seed, GsaInputSplat *out);
+
+/* R/GaussianSplatAsset.cs:152-203 size formulas (+ the 8-byte padding of pos/other,
+ * E/GaussianSplatAssetCreator.cs:815,842). */
+GSA_API int gsa_calc_sizes(uint32_t n, uint32_t pos_fmt, uint32_t scale_fmt, uint32_t color_fmt,
+                           uint32_t sh_fmt, GsaSizes *out);
+
+/* CreateAsset (E/GaussianSplatAssetCreator.cs:248-330): bounds, Morton reorder
+ * (:387-429), chunk min/max + normalise (:520-639) when any stream is lossy (:54-58),
+ * then the five blobs (:705-1066).  `splats` is reordered and modified in place, exactly
+ * like the reference's NativeArray.  Output buffers must have the sizes gsa_calc_sizes
+ * reports; `chunks` may be NULL when the format set is fully float32.
+ * bounds_out: 6 floats (min xyz, max xyz) or NULL. */
+GSA_API int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pos_fmt, uint32_t scale_fmt,
+                             uint32_t color_fmt, uint32_t sh_fmt, void *pos, void *other, void *color,
+                             void *sh, void *chunks, float *bounds_out);
+
+/* Individual pieces, exposed for tests. */
+GSA_API uint64_t gsa_morton_encode3(uint32_t x, uint32_t y, uint32_t z);       /* R/GaussianUtils.cs:81-95 */
+GSA_API uint32_t gsa_splat_index_to_texture_index(uint32_t idx);              /* E/GaussianSplatAssetCreator.cs:863-871 */
+GSA_API void gsa_pack_smallest3(const float q_xyzw[4], float out[4]);         /* R/GaussianUtils.cs:46-76 */
+GSA_API uint32_t gsa_f32tof16(float v);                                       /* Unity.Mathematics math.f32tof16 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

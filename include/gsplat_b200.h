@@ -1,0 +1,206 @@
+/* gsplat_b200.h -- C ABI of the B200-native Gaussian-splat render path.
+ *
+ * This is the drop-in boundary for the hot path of aras-p/UnityGaussianSplatting
+ * (view-calc -> depth sort -> rasterise/blend -> composite).  The reference has no
+ * native plugin: all GPU work is recorded by C# into a Unity
+ * CommandBuffer.  Every entry point below therefore replaces a *C# call site* and
+ * the compute/raster work it dispatches; the citation next to each symbol names it
+ * (paths relative to the reference repo, R/ = package/Runtime, S/ = package/Shaders).
+ *
+ * Rules of the ABI:
+ *   - plain C: pointers, sizes, PODs.  No C++/torch types.
+ *   - every function returns a GsStatus (0 = ok, <0 = error) and never throws or
+ *     aborts; gs_last_error() gives the text.  This mirrors the reference's
+ *     "log and skip" behaviour (R/GaussianSplatRenderer.cs:361-369,447-448,655).
+ *   - one GsContext per CUDA device; calls on one context are serialised by the caller.
+ *     All work is enqueued on the context's stream; only gs_sync/gs_readback_* /
+ *     host-memory images block.
+ *   - matrices are float[16], column-major exactly like UnityEngine.Matrix4x4
+ *     (element (row r, col c) at [c*4 + r]).
+ */
+#ifndef GSPLAT_B200_H
+#define GSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GS_API __declspec(dllexport)
+#else
+#define GS_API __attribute__((visibility("default")))
+#endif
+
+typedef struct GsContext GsContext;
+typedef struct GsAsset GsAsset;
+
+typedef enum GsStatus {
+  GS_OK = 0,
+  GS_ERR_INVALID_ARGUMENT = -1,
+  GS_ERR_CUDA = -2,
+  GS_ERR_OUT_OF_MEMORY = -3,
+  GS_ERR_UNSUPPORTED_FORMAT = -4, /* BC7 colour, clustered SH palettes */
+  GS_ERR_NOT_READY = -5,          /* e.g. gs_render before gs_calc_view */
+  GS_ERR_NO_DEVICE = -6
+} GsStatus;
+
+/* R/GaussianSplatAsset.cs:31-37 (VectorFormat), S/GaussianSplatting.hlsl:319-323 */
+typedef enum GsVectorFormat { GS_VEC_FLOAT32 = 0, GS_VEC_NORM16 = 1, GS_VEC_NORM11 = 2, GS_VEC_NORM6 = 3 } GsVectorFormat;
+/* R/GaussianSplatAsset.cs:51-57 (ColorFormat) */
+typedef enum GsColorFormat { GS_COL_FLOAT32X4 = 0, GS_COL_FLOAT16X4 = 1, GS_COL_NORM8X4 = 2, GS_COL_BC7 = 3 } GsColorFormat;
+/* R/GaussianSplatAsset.cs:70-81 (SHFormat); values >= 4 are clustered palettes */
+typedef enum GsSHFormat { GS_SH_FLOAT32 = 0, GS_SH_FLOAT16 = 1, GS_SH_NORM11 = 2, GS_SH_NORM6 = 3, GS_SH_CLUSTER64K = 4 } GsSHFormat;
+
+/* The asset blobs exactly as GaussianSplatAsset exposes them
+ * (R/GaussianSplatAsset.cs:219-237; uploaded by CreateResourcesForAsset,
+ * R/GaussianSplatRenderer.cs:373-421).  Pointers are HOST memory, borrowed for the
+ * duration of gs_asset_upload; the library copies everything to HBM.
+ * `color` is the 2048-wide, 16x16-Morton-swizzled texture image
+ * (R/GaussianSplatAsset.cs:152-160, S/GaussianSplatting.hlsl:181-194), row-major.
+ * `chunks` may be NULL / chunk_bytes 0 (fully-float32 assets,
+ * R/GaussianSplatRenderer.cs:391-405). */
+typedef struct GsAssetDesc {
+  uint32_t splat_count;
+  uint32_t pos_format, scale_format, sh_format, color_format;
+  const void *pos, *other, *sh, *color, *chunks;
+  uint64_t pos_bytes, other_bytes, sh_bytes, color_bytes, chunk_bytes;
+} GsAssetDesc;
+
+/* R/GaussianCutout.cs:20-40, S/SplatUtilities.compute:96-100 (68 bytes) */
+typedef struct GsCutout {
+  float mat[16];            /* cutout worldToLocal * renderer localToWorld */
+  uint32_t type_and_flags;  /* low byte: 0 ellipsoid, 1 box, 0xFF ignore; 0x100: invert */
+} GsCutout;
+
+/* Per-frame uniforms.  Field-by-field these are the values C# binds in
+ * CalcViewData (R/GaussianSplatRenderer.cs:579-610), SortPoints (:612-639) and
+ * SortAndRenderSplats (:137-149). */
+typedef struct GsFrameParams {
+  float mat_object_to_world[16];  /* tr.localToWorldMatrix            (:587) */
+  float mat_world_to_object[16];  /* tr.worldToLocalMatrix            (:588) */
+  float mat_view[16];             /* cam.worldToCameraMatrix, -z fwd  (:586,:617) */
+  float mat_proj_gpu[16];         /* UNITY_MATRIX_P = GL.GetGPUProjectionMatrix(cam.projectionMatrix, true);
+                                     an engine global in the reference (S/SplatUtilities.compute:200,236) */
+  float screen_w, screen_h;       /* _VecScreenParams.xy              (:591) */
+  float cam_pos_world[3];         /* _VecWorldSpaceCameraPos          (:592) */
+  float splat_scale;              /* m_SplatScale   [0.1,2]           (:599) */
+  float opacity_scale;            /* m_OpacityScale [0.05,20]         (:600) */
+  uint32_t sh_order;              /* m_SHOrder 0..3                   (:601) */
+  uint32_t sh_only;               /* m_SHOnly                         (:602) */
+  uint32_t cutout_count;          /* _SplatCutoutsCount (R/GaussianSplatRenderer.cs:506-508) */
+  uint32_t reserved0;
+  const GsCutout *cutouts;        /* host pointer, cutout_count entries, may be NULL */
+  const uint32_t *deleted_bits;   /* host pointer, ceil(N/32) words or NULL == _SplatBitsValid 0 (:496-501) */
+} GsFrameParams;
+
+typedef enum GsPixelFormat {
+  GS_PIX_RGBA16F = 0,   /* _GaussianSplatRT: R16G16B16A16_SFloat (R/GaussianSplatRenderer.cs:194) */
+  GS_PIX_RGBA32F = 1
+} GsPixelFormat;
+
+typedef enum GsMemory { GS_MEM_HOST = 0, GS_MEM_DEVICE = 1 } GsMemory;
+
+typedef struct GsImage {
+  void *data;
+  uint32_t width, height;
+  uint32_t row_pitch_bytes;  /* 0 = tightly packed */
+  uint32_t format;           /* GsPixelFormat */
+  uint32_t memory;           /* GsMemory: where `data` lives */
+} GsImage;
+
+/* How the render-target blend is evaluated.
+ * GS_BLEND_FP16_ROP reproduces the reference: the RT is RGBA16F, so the fixed-function
+ * blender (Blend OneMinusDstAlpha One, S/RenderGaussianSplats.shader:11) rounds dst to
+ * half after EVERY splat.  GS_BLEND_FP32 keeps dst in float32 registers and rounds once. */
+typedef enum GsBlendMode { GS_BLEND_FP16_ROP = 0, GS_BLEND_FP32 = 1 } GsBlendMode;
+
+typedef struct GsRenderOptions {
+  uint32_t blend_mode;        /* GsBlendMode */
+  uint32_t reserved;
+  /* Screen-tile partition for multi-GPU: this context composites only
+   * tile rows r with (r / band_rows) % partition_count == partition_index.
+   * partition_count 0 or 1 = whole image. */
+  uint32_t partition_index, partition_count, band_rows, reserved1;
+} GsRenderOptions;
+
+/* Per-stage device times of the last gs_frame/gs_sort/gs_calc_view/gs_render call with
+ * timing enabled (GaussianSplat.Sort / CalcView / Draw / Compose profiler markers,
+ * R/GaussianSplatRenderer.cs:20-22,287).  Milliseconds, CUDA events on the context stream. */
+typedef struct GsStageTimes {
+  float distances_ms, sort_ms, view_ms, bin_ms, raster_ms, composite_ms, total_ms;
+  float sort_pass_ms[4];
+  uint64_t tile_entries;      /* (tile, splat) pairs produced by binning */
+  uint32_t kernel_launches;   /* kernels of this library launched by the call */
+  uint32_t reserved;
+} GsStageTimes;
+
+/* ---- lifetime ---------------------------------------------------------------- */
+/* EnsureSorterAndRegister + resource setup, R/GaussianSplatRenderer.cs:450-475.
+ * stream_handle: an existing cudaStream_t to enqueue on (0 = create a private stream). */
+GS_API int gs_create(int cuda_device, void *stream_handle, GsContext **out);
+GS_API void gs_destroy(GsContext *ctx);
+GS_API const char *gs_last_error(GsContext *ctx); /* ctx may be NULL: last global error */
+GS_API int gs_sync(GsContext *ctx);
+GS_API int gs_set_timing(GsContext *ctx, int enabled);
+GS_API int gs_get_stage_times(GsContext *ctx, GsStageTimes *out);
+GS_API const char *gs_version(void);
+
+/* ---- asset --------------------------------------------------------------------- */
+/* CreateResourcesForAsset + InitSortBuffers + CSSetIndices,
+ * R/GaussianSplatRenderer.cs:373-445, S/SplatUtilities.compute:59-67 */
+GS_API int gs_asset_upload(GsContext *ctx, const GsAssetDesc *desc, GsAsset **out);
+/* DisposeResourcesForAsset / OnDisable, R/GaussianSplatRenderer.cs:533-577 */
+GS_API void gs_asset_destroy(GsAsset *asset);
+/* CSSetIndices: order[i] = i (S/SplatUtilities.compute:59-67) */
+GS_API int gs_asset_reset_order(GsAsset *asset);
+GS_API uint32_t gs_asset_splat_count(const GsAsset *asset);
+
+/* ---- the hot path -------------------------------------------------------------- */
+/* SortPoints: CSCalcDistances + GpuSorting.Dispatch
+ * (R/GaussianSplatRenderer.cs:612-639, S/SplatUtilities.compute:69-82,
+ *  R/GpuSorting.cs:142-198).  The order buffer persists across calls: distances are
+ * gathered through the previous order and the sort is stable, exactly as the reference. */
+GS_API int gs_sort(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp);
+/* CalcViewData: CSCalcViewData (R/GaussianSplatRenderer.cs:579-610,
+ * S/SplatUtilities.compute:189-252) */
+GS_API int gs_calc_view(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp);
+/* cmb.DrawProcedural(matSplats, 6 idx, N instances) into the cleared _GaussianSplatRT
+ * (R/GaussianSplatRenderer.cs:156-165,194-196; S/RenderGaussianSplats.shader).
+ * Output: premultiplied RGBA (format/memory per `rt`).  Requires gs_calc_view first. */
+GS_API int gs_render(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp,
+                     const GsRenderOptions *opt, GsImage *rt);
+/* Composite pass: GaussianComposite.shader:35-39 with Blend SrcAlpha OneMinusSrcAlpha
+ * (R/GaussianSplatRenderer.cs:206-210).  `camera_target` is read-modify-write. */
+GS_API int gs_composite(GsContext *ctx, const GsImage *rt, GsImage *camera_target);
+/* SortAndRenderSplats for one renderer, one stream, no host round trips:
+ * (do_sort ? gs_sort : nothing) -> gs_calc_view -> gs_render [-> gs_composite if
+ * camera_target != NULL].  do_sort == (m_FrameCounter % m_SortNthFrame == 0),
+ * R/GaussianSplatRenderer.cs:120-121.  rt may be NULL when camera_target is given
+ * (the RT then lives only in library scratch). */
+GS_API int gs_frame(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp,
+                    const GsRenderOptions *opt, int do_sort, GsImage *rt, GsImage *camera_target);
+
+/* ---- stand-alone sorter (GpuSorting.Dispatch, R/GpuSorting.cs:142-198) ----------- */
+/* Stable ascending sort of `count` (uint32 key, uint32 payload) pairs in place in DEVICE
+ * buffers keys/payload (KEY_UINT PAYLOAD_UINT SHOULD_ASCEND SORT_PAIRS, R/GpuSorting.cs:115-128). */
+GS_API int gs_sort_pairs_device(GsContext *ctx, uint32_t *d_keys, uint32_t *d_payload, uint32_t count);
+/* Same through HOST buffers (copies in, sorts, copies out, blocks). */
+GS_API int gs_sort_pairs_host(GsContext *ctx, uint32_t *keys, uint32_t *payload, uint32_t count);
+
+/* ---- test hooks (blocking device->host reads) ----------------------------------- */
+GS_API int gs_readback_order(GsAsset *asset, uint32_t *dst);      /* _SplatSortKeys, N words */
+GS_API int gs_readback_keys(GsAsset *asset, uint32_t *dst);       /* _SplatSortDistances, N words (sorted after gs_sort) */
+GS_API int gs_readback_view(GsAsset *asset, void *dst);           /* _SplatViewData, N x 40 bytes (S/GaussianSplatting.hlsl:610-615) */
+GS_API int gs_upload_order(GsAsset *asset, const uint32_t *src);  /* seed a previous-frame order */
+
+/* ---- device-pointer access for zero-copy hosts (torch / CUDA-Vulkan interop) ----- */
+GS_API void *gs_context_stream(GsContext *ctx);
+GS_API void *gs_asset_device_ptr(GsAsset *asset, int which); /* 0 order, 1 keys, 2 view */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H */

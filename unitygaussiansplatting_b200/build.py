@@ -1,0 +1,101 @@
+"""In-tree native build of the three shared libraries.
+
+  libgsplat_b200.so   CUDA hot path + C ABI (include/gsplat_b200.h), sm_100a only
+  libgsplat_asset.so  host-side asset packer / synthetic scenes (include/gsplat_asset.h)
+  oracle/libgs_oracle.so  CPU oracle -- test infrastructure, built by its own Makefile
+
+Everything is compiled by explicit nvcc / g++ command lines (no JIT cache), so the
+artefacts travel with the tree to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+NATIVE_LIB = PKG / "libgsplat_b200.so"
+ASSET_LIB = PKG / "libgsplat_asset.so"
+ORACLE_DIR = ROOT / "oracle"
+ORACLE_LIB = ORACLE_DIR / "libgs_oracle.so"
+
+CU_SOURCES = ["gs_api.cu", "gs_view.cu", "gs_sort.cu", "gs_raster.cu"]
+CU_HEADERS = ["gs_common.cuh", "gs_kernels.cuh", "../../include/gsplat_b200.h"]
+
+
+def _host_cxx() -> str:
+    for c in ("/usr/bin/g++", shutil.which("g++") or ""):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("no g++ found")
+
+
+def _nvcc() -> str:
+    for c in ("/usr/local/cuda/bin/nvcc", shutil.which("nvcc") or ""):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+
+
+def _stale(target: Path, sources) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(s).stat().st_mtime > t for s in sources)
+
+
+def _run(cmd, cwd=None):
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(map(str, cmd)), r.stdout))
+    return r.stdout
+
+
+def nvcc_flags(extra=()):
+    return [
+        "-gencode", "arch=compute_100a,code=sm_100a",
+        "-O3", "-std=c++17", "-lineinfo",
+        "-fmad=false",  # arithmetic contract: FMAs only where fmaf() is written
+        "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
+        "-ccbin", _host_cxx(),
+        *extra,
+    ]
+
+
+def build_native(force: bool = False, verbose: bool = False) -> Path:
+    srcs = [CSRC / s for s in CU_SOURCES]
+    deps = srcs + [CSRC / h for h in CU_HEADERS]
+    if force or _stale(NATIVE_LIB, deps):
+        extra = ["-Xptxas", "-v"] if verbose else []
+        out = _run([_nvcc(), *nvcc_flags(extra), "-shared", "-o", str(NATIVE_LIB), *map(str, srcs)])
+        if verbose:
+            print(out)
+    return NATIVE_LIB
+
+
+def build_asset(force: bool = False) -> Path:
+    src = CSRC / "asset_creator.cpp"
+    if force or _stale(ASSET_LIB, [src, ROOT / "include" / "gsplat_asset.h"]):
+        _run([_host_cxx(), "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",
+              "-o", str(ASSET_LIB), str(src)])
+    return ASSET_LIB
+
+
+def build_oracle(force: bool = False) -> Path:
+    if force and ORACLE_LIB.exists():
+        ORACLE_LIB.unlink()
+    _run(["make", "-C", str(ORACLE_DIR)])
+    return ORACLE_LIB
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    return build_native(force, verbose), build_asset(force), build_oracle(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built:", NATIVE_LIB, ASSET_LIB, ORACLE_LIB)

@@ -1,0 +1,90 @@
+// gs_kernels.cuh -- declarations shared between the .cu translation units.
+#pragma once
+#include "gs_common.cuh"
+
+namespace gs {
+
+constexpr uint32_t kRectEmpty = 0xFFFFFFFFu;  // tile rect sentinel (tile indices are < 255)
+
+// Screen-space footprint of one splat, derived from its SplatViewData exactly the way the
+// draw stage defines it (S/RenderGaussianSplats.shader:35-77; DESIGN.md "Raster rule").
+struct SplatFootprint {
+  float cx, cy;              // centre, pixels (D3D viewport: x right, y down)
+  float i1x, i1y, i2x, i2y;  // axis / |axis|^2 : quad coordinates q = (dot(d,i1), dot(d,i2))
+  float hx, hy;              // conservative half extents of the visible part, pixels
+  float ca;                  // opacity (half -> float)
+};
+
+__device__ __forceinline__ bool splat_footprint(float4 clip, float a1x, float a1y, float a2x, float a2y, float ca, float W,
+                                                float H, SplatFootprint &fp) {
+  if (!(clip.w > 0.0f)) return false;  // behindCam -> NaN vertex -> primitive dropped (shader :41-45)
+  if (!(ca >= 0.0f)) return false;     // "selected" branch (col.a = -1) needs valid edit bits: out of scope
+  float ndx = __fdiv_rn(clip.x, clip.w), ndy = __fdiv_rn(clip.y, clip.w);
+  float cx = fmaf(ndx, 0.5f, 0.5f) * W, cy = fmaf(ndy, -0.5f, 0.5f) * H;
+  float ex = 2.0f * (fabsf(a1x) + fabsf(a2x)), ey = 2.0f * (fabsf(a1y) + fabsf(a2y));
+  if (!(ex < 1.0e6f) || !(ey < 1.0e6f) || !(fabsf(cx) < 1.0e7f) || !(fabsf(cy) < 1.0e7f)) return false;
+  // alpha = sat(exp(-r2) * ca) can only reach 1/255 if ca does (exp_neg(0) = 1.00000012)
+  if (ca < 0.00392f) return false;
+  float n1 = a1x * a1x + a1y * a1y, n2 = a2x * a2x + a2y * a2y;
+  fp.cx = cx; fp.cy = cy;
+  fp.i1x = __fdiv_rn(a1x, n1); fp.i1y = __fdiv_rn(a1y, n1);
+  fp.i2x = __fdiv_rn(a2x, n2); fp.i2y = __fdiv_rn(a2y, n2);
+  fp.ca = ca;
+  // visible part: the +-2 quad intersected with {r2 <= ln(255*ca)} (discard at alpha < 1/255)
+  float r2 = fminf(__logf(ca * 255.0f) * 1.001f + 2.0e-3f, 8.0f);
+  float rq = sqrtf(fmaxf(r2, 0.0f));
+  float exE = rq * sqrtf(a1x * a1x + a2x * a2x), eyE = rq * sqrtf(a1y * a1y + a2y * a2y);
+  fp.hx = fminf(ex, exE) * 1.0001f + 0.01f;
+  fp.hy = fminf(ey, eyE) * 1.0001f + 0.01f;
+  return true;
+}
+
+// Pixel rows/cols whose centres can be touched -> inclusive tile rectangle packed x0|y0<<8|x1<<16|y1<<24.
+__device__ __forceinline__ uint32_t footprint_tile_rect(const SplatFootprint &fp, const FrameConsts &fc) {
+  float x0 = fmaxf(ceilf(fp.cx - fp.hx - 0.5f), 0.0f), x1 = fminf(floorf(fp.cx + fp.hx - 0.5f), fc.screenW - 1.0f);
+  float y0 = fmaxf(ceilf(fp.cy - fp.hy - 0.5f), 0.0f), y1 = fminf(floorf(fp.cy + fp.hy - 0.5f), fc.screenH - 1.0f);
+  if (!(x0 <= x1) || !(y0 <= y1)) return kRectEmpty;
+  uint32_t tx0 = (uint32_t)x0 >> 4, tx1 = (uint32_t)x1 >> 4, ty0 = (uint32_t)y0 >> 4, ty1 = (uint32_t)y1 >> 4;
+  return tx0 | (ty0 << 8) | (tx1 << 16) | (ty1 << 24);
+}
+
+// ---- launchers (each enqueues on `s`, returns nothing; errors surface via cudaGetLastError) ----
+void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s);
+void launch_calc_distances(const AssetView &a, const FrameConsts &fc, const uint32_t *order, uint32_t *keys, uint32_t *ghist,
+                           cudaStream_t s);
+void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
+                      uint32_t *rect, cudaStream_t s);
+
+// Radix sort (gs_sort.cu).  Scratch layout is owned by the caller (gs_api.cu).
+struct SortScratch {
+  uint32_t *alt_keys, *alt_vals;  // ping-pong buffers, >= capacity elements each
+  uint32_t *ghist;                // 4*256 digit counts (one row per pass)
+  uint32_t *lookback;             // passes * max_tiles * 256 status words
+  uint32_t *tickets;              // passes counters
+  uint32_t max_tiles;             // capacity / kSortTileItems rounded up
+};
+constexpr uint32_t kSortTileItems = 4096;  // 256 threads x 16 keys
+size_t sort_lookback_words(uint32_t capacity, int passes);
+// Stable ascending LSD sort of (key,val) pairs on bits [0, 8*passes).  count is read from
+// d_count (device) so the binner can sort a device-sized list; capacity bounds the grid.
+// ghist must already hold the per-pass digit counts when hist_ready, otherwise it is computed.
+// After an even number of passes the result is back in keys/vals.
+void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, uint32_t capacity, int passes, bool hist_ready,
+                       const SortScratch &sc, cudaStream_t s, cudaEvent_t *pass_events = nullptr);
+
+// Binning + raster + composite (gs_raster.cu)
+struct BinScratch {
+  uint32_t *block_sums;    // scan partials
+  uint32_t *entry_count;   // [0] = total (tile,splat) entries, [1] = overflow flag
+  uint32_t *tile_keys, *tile_vals;  // capacity entries each
+  uint32_t *tile_start;    // tiles+1
+  uint32_t capacity;
+};
+void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
+                    const BinScratch &bs, const SortScratch &sc, cudaStream_t s);
+void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const uint32_t *view, const BinScratch &bs, void *rt,
+                   uint32_t rt_pitch_bytes, uint32_t rt_format, const void *unused, cudaStream_t s);
+void launch_composite(const void *rt, uint32_t rt_pitch, uint32_t rt_format, void *target, uint32_t tgt_pitch, uint32_t tgt_format,
+                      uint32_t W, uint32_t H, cudaStream_t s);
+
+}  // namespace gs

@@ -1,0 +1,376 @@
+// gs_raster.cu -- tile binning, front-to-back compositing and the final composite pass.
+//
+// The reference draws one instanced quad per splat through the hardware rasteriser with
+// fixed-function blending `Blend OneMinusDstAlpha One` into an RGBA16F target
+// (S/RenderGaussianSplats.shader:10-12,35-108; draw call R/GaussianSplatRenderer.cs:156-165).
+// A CUDA device has neither rasteriser nor ROP, so the same pixels are produced by:
+//   1. bin   -- walk the splats in sorted order; each emits one (tile id, splat id) entry per
+//               16x16 screen tile its visible footprint can touch (rect written by
+//               k_calc_view).  Emission order == depth order, so one STABLE 16-bit radix sort
+//               by tile id (2 onesweep passes) yields per-tile lists that are already in
+//               draw order.  No 64-bit (tile|depth) re-sort of duplicated keys.
+//   2. raster-- one CTA per tile, one pixel per thread.  The tile's list is consumed in
+//               batches staged in shared memory; every warp owns an 8x4 pixel block and
+//               first culls a batch against that block with one ballot per 32 splats, so
+//               small splats cost 1/32 of a pixel evaluation where they do not land.
+//               Blending reproduces the ROP: dst = src*(1-dst.a) + dst, rounded to half after
+//               every splat (GS_BLEND_FP16_ROP) -- or kept in float32 (GS_BLEND_FP32).
+//   3. composite (S/GaussianComposite.shader:35-39).
+#include "gs_kernels.cuh"
+
+namespace gs {
+
+// ---- screen-tile partition helpers (multi-GPU bands) ---------------------------
+struct Partition {
+  uint32_t index, count, band;  // count <= 1: everything is ours
+  __host__ __device__ uint32_t own_rows_below(uint32_t y) const {  // # own tile rows in [0, y)
+    if (count <= 1) return y;
+    uint32_t cyc = band * count, q = y / cyc, r = y % cyc;
+    uint32_t lo = index * band;
+    uint32_t in = r > lo ? (r - lo < band ? r - lo : band) : 0u;
+    return q * band + in;
+  }
+  __host__ __device__ bool owns(uint32_t y) const { return count <= 1 || (y / band) % count == index; }
+  __host__ __device__ uint32_t kth_own_row(uint32_t k) const {
+    if (count <= 1) return k;
+    return ((k / band) * count + index) * band + (k % band);
+  }
+};
+static Partition make_partition(const GsRenderOptions &o) {
+  Partition p;
+  p.count = o.partition_count;
+  p.index = o.partition_count > 1 ? o.partition_index : 0;
+  p.band = o.band_rows ? o.band_rows : 1;
+  return p;
+}
+
+__device__ __forceinline__ uint32_t rect_entries(uint32_t r, const Partition &p) {
+  if (r == kRectEmpty) return 0;
+  uint32_t x0 = r & 255u, y0 = (r >> 8) & 255u, x1 = (r >> 16) & 255u, y1 = r >> 24;
+  uint32_t rows = p.own_rows_below(y1 + 1) - p.own_rows_below(y0);
+  return rows * (x1 - x0 + 1);
+}
+
+constexpr int kBinItems = 4;
+constexpr int kBinBlock = 256 * kBinItems;
+
+// ---- 1a. per-block entry totals ---------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bin_count(const uint32_t *__restrict__ order, const uint32_t *__restrict__ rect, uint32_t n,
+                                                   Partition part, uint32_t *__restrict__ block_sums) {
+  __shared__ uint32_t s_w[8];
+  uint32_t sum = 0;
+  const uint32_t base = blockIdx.x * kBinBlock + threadIdx.x * kBinItems;
+#pragma unroll
+  for (int i = 0; i < kBinItems; ++i) {
+    uint32_t r = base + i;
+    if (r < n) sum += rect_entries(__ldg(rect + __ldg(order + r)), part);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+// ---- 1b. exclusive scan of the block totals (single CTA) ---------------------------------------
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *__restrict__ block_sums, uint32_t nblocks, uint32_t capacity,
+                                                   uint32_t *__restrict__ entry_count) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < nblocks; base += 1024) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = (i < nblocks) ? block_sums[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_w[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= (uint32_t)o) wi += t;
+      }
+      s_w[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t excl = s_carry + s_w[warp] + inc - v;
+    if (i < nblocks) block_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    uint32_t total = s_carry;
+    entry_count[1] = total > capacity ? 1u : 0u;  // overflow: lists are truncated, the API reports it
+    entry_count[0] = total > capacity ? capacity : total;
+  }
+}
+
+// ---- 1c. emit (tile id, splat id) entries in depth order ----------------------------------------
+__device__ __forceinline__ void emit_entry(uint32_t e, uint32_t r, uint32_t id, uint32_t off, const Partition &p, uint32_t tilesX,
+                                           uint32_t capacity, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  const uint32_t x0 = r & 255u, y0 = (r >> 8) & 255u, x1 = (r >> 16) & 255u;
+  const uint32_t w = x1 - x0 + 1;
+  const uint32_t krow = e / w, tx = x0 + (e - krow * w);
+  const uint32_t ty = p.kth_own_row(p.own_rows_below(y0) + krow);
+  const uint32_t o = off + e;
+  if (o < capacity) {
+    keys[o] = ty * tilesX + tx;
+    vals[o] = id;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ order, const uint32_t *__restrict__ rect, uint32_t n,
+                                                  Partition part, uint32_t tilesX, const uint32_t *__restrict__ block_sums,
+                                                  uint32_t capacity, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  __shared__ uint32_t s_w[8];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t base = blockIdx.x * kBinBlock + threadIdx.x * kBinItems;
+  uint32_t id[kBinItems], rc[kBinItems], cnt[kBinItems], sum = 0;
+#pragma unroll
+  for (int i = 0; i < kBinItems; ++i) {
+    uint32_t r = base + i;
+    id[i] = 0; rc[i] = kRectEmpty; cnt[i] = 0;
+    if (r < n) {
+      id[i] = __ldg(order + r);
+      rc[i] = __ldg(rect + id[i]);
+      cnt[i] = rect_entries(rc[i], part);
+    }
+    sum += cnt[i];
+  }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += t;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (uint32_t w = 0; w < warp; ++w) woff += s_w[w];
+  uint32_t off = block_sums[blockIdx.x] + woff + inc - sum;
+#pragma unroll
+  for (int i = 0; i < kBinItems; ++i) {
+    // small footprints: the owning lane writes them; large ones are spread over the warp
+    const bool big = cnt[i] > 8;
+    if (!big)
+      for (uint32_t e = 0; e < cnt[i]; ++e) emit_entry(e, rc[i], id[i], off, part, tilesX, capacity, keys, vals);
+    uint32_t bigmask = __ballot_sync(0xffffffffu, big);
+    while (bigmask) {
+      const int src = __ffs(bigmask) - 1;
+      bigmask &= bigmask - 1;
+      const uint32_t c = __shfl_sync(0xffffffffu, cnt[i], src), r = __shfl_sync(0xffffffffu, rc[i], src),
+                     d = __shfl_sync(0xffffffffu, id[i], src), o = __shfl_sync(0xffffffffu, off, src);
+      for (uint32_t e = lane; e < c; e += 32) emit_entry(e, r, d, o, part, tilesX, capacity, keys, vals);
+    }
+    off += cnt[i];
+  }
+}
+
+// ---- 1d. per-tile [start,end) after the stable sort by tile id -----------------------------------
+__global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ entry_count,
+                                                     uint2 *__restrict__ ranges) {
+  const uint32_t m = entry_count[0];
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < m; i += gridDim.x * 256) {
+    const uint32_t k = keys[i];
+    if (i == 0 || keys[i - 1] != k) ranges[k].x = i;
+    if (i + 1 == m || keys[i + 1] != k) ranges[k].y = i + 1;
+  }
+}
+
+void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
+                    const BinScratch &bs, const SortScratch &sc, cudaStream_t s) {
+  const Partition part = make_partition(opt);
+  const uint32_t tiles = fc.tilesX * fc.tilesY;
+  cudaMemsetAsync(bs.tile_start, 0, (size_t)tiles * sizeof(uint2), s);
+  if (!n) { cudaMemsetAsync(bs.entry_count, 0, 8, s); return; }
+  const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
+  k_bin_count<<<nblocks, 256, 0, s>>>(order, rect, n, part, bs.block_sums);
+  k_bin_scan<<<1, 1024, 0, s>>>(bs.block_sums, nblocks, bs.capacity, bs.entry_count);
+  k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, n, part, fc.tilesX, bs.block_sums, bs.capacity, bs.tile_keys, bs.tile_vals);
+  launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, 2, false, sc, s);
+  k_tile_ranges<<<148 * 8, 256, 0, s>>>(bs.tile_keys, bs.entry_count, reinterpret_cast<uint2 *>(bs.tile_start));
+}
+
+// ---- 2. raster ---------------------------------------------------------------------------------
+__device__ __forceinline__ float round_half(float v) { return __half2float(__float2half_rn(v)); }
+
+template <bool FP16_ROP, int OUT_FMT>
+__global__ void __launch_bounds__(256)
+k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, const uint32_t *__restrict__ tile_vals,
+         const uint2 *__restrict__ ranges, uint8_t *__restrict__ rt, uint32_t pitch) {
+  __shared__ float4 s_a[256];  // cx, cy, i1x, i1y
+  __shared__ float4 s_b[256];  // i2x, i2y, opacity, hx
+  __shared__ float4 s_c[256];  // r, g, b, hy
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tx = blockIdx.x, ty = part.kth_own_row(blockIdx.y);
+  const uint2 range = ranges[ty * fc.tilesX + tx];
+  const uint32_t bx = tx * kTile + (warp & 1) * 8, by = ty * kTile + (warp >> 1) * 4;
+  const uint32_t px = bx + (lane & 7), py = by + (lane >> 3);
+  const float pxc = (float)px + 0.5f, pyc = (float)py + 0.5f;
+  const float bcx = (float)bx + 4.0f, bcy = (float)by + 2.0f;
+  const bool in_image = px < (uint32_t)fc.screenW && py < (uint32_t)fc.screenH;
+
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;  // ClearRenderTarget(0,0,0,0), R/GaussianSplatRenderer.cs:196
+
+  // software pipeline: the next batch's records are in flight while this one is composited
+  float2 r0, r1, r2, r3;
+  uint2 rcol;
+  bool have = false;
+  auto prefetch = [&](uint32_t e) {
+    have = e < range.y;
+    if (have) {
+      const uint32_t id = __ldg(tile_vals + e);
+      const float2 *p = reinterpret_cast<const float2 *>(view + (size_t)id * 10);  // 40-byte stride: 8-byte aligned
+      r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2); r3 = __ldg(p + 3);
+      rcol = __ldg(reinterpret_cast<const uint2 *>(p + 4));
+    }
+  };
+  prefetch(range.x + tid);
+
+  for (uint32_t base = range.x; base < range.y; base += 256) {
+    {  // stage the prefetched record as a footprint
+      SplatFootprint fp;
+      bool ok = false;
+      float cr = 0.f, cg = 0.f, cb = 0.f;
+      if (have) {
+        ok = splat_footprint(make_float4(r0.x, r0.y, r1.x, r1.y), r2.x, r2.y, r3.x, r3.y, f16lo(rcol.y), fc.screenW, fc.screenH, fp);
+        cr = f16hi(rcol.x); cg = f16lo(rcol.x); cb = f16hi(rcol.y);  // shader :48-51
+      }
+      if (!ok) { fp.cx = fp.cy = fp.i1x = fp.i1y = fp.i2x = fp.i2y = fp.ca = 0.f; fp.hx = fp.hy = -1.0e9f; }
+      s_a[tid] = make_float4(fp.cx, fp.cy, fp.i1x, fp.i1y);
+      s_b[tid] = make_float4(fp.i2x, fp.i2y, fp.ca, fp.hx);
+      s_c[tid] = make_float4(cr, cg, cb, fp.hy);
+    }
+    __syncthreads();
+    prefetch(base + 256 + tid);
+
+    const uint32_t cnt = min(256u, range.y - base);
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+      // one ballot culls 32 splats against this warp's 8x4 pixel block
+      const uint32_t e = c0 + lane;
+      bool hit = false;
+      if (e < cnt) {
+        const float4 A = s_a[e];
+        const float hx = s_b[e].w, hy = s_c[e].w;
+        hit = (fabsf(A.x - bcx) <= hx + 3.5f) && (fabsf(A.y - bcy) <= hy + 1.5f);
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        const uint32_t j = c0 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float4 A = s_a[j], B = s_b[j];
+        const float dx = pxc - A.x, dy = A.y - pyc;  // pixel y grows down, NDC y up
+        const float qa = fmaf(dy, A.w, dx * A.z), qb = fmaf(dy, B.y, dx * B.x);
+        const bool inside = (fabsf(qa) <= 2.0f) && (fabsf(qb) <= 2.0f);  // quad corners at +-2 (:54-55)
+        if (!__any_sync(0xffffffffu, inside)) continue;
+        const float power = -fmaf(qb, qb, qa * qa);                       // -dot(i.pos, i.pos) (:81)
+        const float alpha = satf(exp_neg(power) * B.z);                   // :82-86
+        if (inside && alpha >= 0.003921569f) {                            // discard below 1/255 (:103-104)
+          const float4 C = s_c[j];
+          const float om = 1.0f - d3;                                     // Blend OneMinusDstAlpha One (:11)
+          float n0 = fmaf(C.x * alpha, om, d0), n1 = fmaf(C.y * alpha, om, d1), n2 = fmaf(C.z * alpha, om, d2),
+                n3 = fmaf(alpha, om, d3);
+          if (FP16_ROP) { n0 = round_half(n0); n1 = round_half(n1); n2 = round_half(n2); n3 = round_half(n3); }
+          d0 = n0; d1 = n1; d2 = n2; d3 = n3;
+        }
+      }
+    }
+    // a pixel whose dst.a == 1 ignores every later splat exactly (src*0 + dst): safe early out
+    if (__syncthreads_and(d3 == 1.0f || !in_image)) break;
+  }
+
+  if (in_image) {
+    uint8_t *row = rt + (size_t)py * pitch;
+    if (OUT_FMT == GS_PIX_RGBA16F) {
+      uint2 o;
+      o.x = f32tof16(d0) | (f32tof16(d1) << 16);
+      o.y = f32tof16(d2) | (f32tof16(d3) << 16);
+      reinterpret_cast<uint2 *>(row)[px] = o;
+    } else {
+      reinterpret_cast<float4 *>(row)[px] = make_float4(d0, d1, d2, d3);
+    }
+  }
+}
+
+void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const uint32_t *view, const BinScratch &bs, void *rt,
+                   uint32_t rt_pitch_bytes, uint32_t rt_format, const void *, cudaStream_t s) {
+  const Partition part = make_partition(opt);
+  const uint32_t rows = part.own_rows_below(fc.tilesY);
+  if (!rows || !fc.tilesX) return;
+  dim3 grid(fc.tilesX, rows);
+  const uint2 *ranges = reinterpret_cast<const uint2 *>(bs.tile_start);
+  const bool rop = opt.blend_mode == GS_BLEND_FP16_ROP;
+  uint8_t *out = reinterpret_cast<uint8_t *>(rt);
+  if (rt_format == GS_PIX_RGBA16F) {
+    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes);
+    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes);
+  } else {
+    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes);
+    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes);
+  }
+}
+
+// ---- 3. composite (S/GaussianComposite.shader:35-39, Blend SrcAlpha OneMinusSrcAlpha :11) ------
+__device__ __forceinline__ float gamma_to_linear(float x) {  // UnityCG.cginc GammaToLinearSpace (not vendored)
+  return x * fmaf(x, fmaf(x, 0.305306011f, 0.682171111f), 0.012522878f);
+}
+
+__global__ void __launch_bounds__(256) k_composite(const uint8_t *__restrict__ rt, uint32_t rt_pitch, uint32_t rt_fmt,
+                                                   uint8_t *__restrict__ tgt, uint32_t tgt_pitch, uint32_t tgt_fmt, uint32_t W,
+                                                   uint32_t H) {
+  const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  float4 c;
+  if (rt_fmt == GS_PIX_RGBA16F) {
+    uint2 v = reinterpret_cast<const uint2 *>(rt + (size_t)y * rt_pitch)[x];
+    c = make_float4(f16lo(v.x), f16hi(v.x), f16lo(v.y), f16hi(v.y));
+  } else {
+    c = reinterpret_cast<const float4 *>(rt + (size_t)y * rt_pitch)[x];
+  }
+  if (!(c.w > 0.0f)) return;  // SrcAlpha == 0 leaves the target untouched
+  float4 d;
+  if (tgt_fmt == GS_PIX_RGBA16F) {
+    uint2 v = reinterpret_cast<const uint2 *>(tgt + (size_t)y * tgt_pitch)[x];
+    d = make_float4(f16lo(v.x), f16hi(v.x), f16lo(v.y), f16hi(v.y));
+  } else {
+    d = reinterpret_cast<const float4 *>(tgt + (size_t)y * tgt_pitch)[x];
+  }
+  const float a = c.w, om = 1.0f - a;
+  float4 o;
+  o.x = fmaf(gamma_to_linear(__fdiv_rn(c.x, a)), a, d.x * om);
+  o.y = fmaf(gamma_to_linear(__fdiv_rn(c.y, a)), a, d.y * om);
+  o.z = fmaf(gamma_to_linear(__fdiv_rn(c.z, a)), a, d.z * om);
+  o.w = fmaf(a, a, d.w * om);
+  if (tgt_fmt == GS_PIX_RGBA16F) {
+    uint2 v;
+    v.x = f32tof16(o.x) | (f32tof16(o.y) << 16);
+    v.y = f32tof16(o.z) | (f32tof16(o.w) << 16);
+    reinterpret_cast<uint2 *>(tgt + (size_t)y * tgt_pitch)[x] = v;
+  } else {
+    reinterpret_cast<float4 *>(tgt + (size_t)y * tgt_pitch)[x] = o;
+  }
+}
+
+void launch_composite(const void *rt, uint32_t rt_pitch, uint32_t rt_format, void *target, uint32_t tgt_pitch, uint32_t tgt_format,
+                      uint32_t W, uint32_t H, cudaStream_t s) {
+  if (!W || !H) return;
+  dim3 grid((W + 31) / 32, (H + 7) / 8);
+  k_composite<<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t *>(rt), rt_pitch, rt_format, reinterpret_cast<uint8_t *>(target),
+                                   tgt_pitch, tgt_format, W, H);
+}
+
+}  // namespace gs

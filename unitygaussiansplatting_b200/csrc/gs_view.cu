@@ -1,0 +1,387 @@
+// gs_view.cu -- CSSetIndices, CSCalcDistances, CSCalcViewData as sm_100a kernels.
+//
+// Reference behaviour: S/SplatUtilities.compute:59-82,107-252 and the decode library
+// S/GaussianSplatting.hlsl:5-11,29-90,130-229,261-300,346-608.  Design (not a port):
+//   * one CTA == one 256-splat chunk, so the 64-byte chunk header is fetched once per CTA
+//     into shared memory and broadcast; every packed stream is read with the widest
+//     aligned vector load its stride allows;
+//   * the 40-byte SplatViewData records of a CTA are staged in shared memory and leave as
+//     fully coalesced 16-byte stores (a 40-byte stride cannot be stored with float4);
+//   * the same kernel emits the splat's screen-tile rectangle (4 bytes) for the binner,
+//     so the raster stage never has to touch the 40-byte record to count tiles;
+//   * CSCalcDistances also accumulates the four 8-bit digit histograms of the keys it
+//     writes, which removes the radix sort's separate histogram read (4 B/splat).
+#include "gs_kernels.cuh"
+
+namespace gs {
+
+__global__ void __launch_bounds__(256) k_set_indices(uint32_t *__restrict__ order, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[i] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// CSCalcDistances (+ fused digit histograms for the sort)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 load_pos(const AssetView &a, uint32_t idx) {
+  float3 p = load_vector(a.pos, (uint64_t)idx * vec_stride(a.posFmt), a.posFmt);
+  uint32_t ci = idx >> 8;
+  if (ci < a.chunkCount) {  // LoadSplatPos, S/GaussianSplatting.hlsl:409-421
+    const float4 *c = reinterpret_cast<const float4 *>(a.chunks + ci);
+    float4 px_py = __ldg(c + 1);  // posX.xy posY.xy
+    float2 pz = __ldg(reinterpret_cast<const float2 *>(c + 2));
+    p.x = lerpf(px_py.x, px_py.y, p.x);
+    p.y = lerpf(px_py.z, px_py.w, p.y);
+    p.z = lerpf(pz.x, pz.y, p.z);
+  }
+  return p;
+}
+
+constexpr int kDistItems = 4;  // keys per thread
+
+__global__ void __launch_bounds__(256) k_calc_distances(AssetView a, float4 row, const uint32_t *__restrict__ order,
+                                                        uint32_t *__restrict__ keys, uint32_t *__restrict__ ghist) {
+  __shared__ uint32_t sh[4 * 256];
+  for (int i = threadIdx.x; i < 1024; i += 256) sh[i] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * (256 * kDistItems);
+#pragma unroll
+  for (int it = 0; it < kDistItems; ++it) {
+    uint32_t i = base + it * 256 + threadIdx.x;
+    if (i < a.n) {
+      uint32_t o = __ldg(order + i);  // gather through the previous order, S/SplatUtilities.compute:76
+      float3 p = load_pos(a, o);
+      float z = fmaf(row.z, p.z, fmaf(row.y, p.y, fmaf(row.x, p.x, row.w)));
+      uint32_t k = float_to_sortable_uint(z);
+      keys[i] = k;
+      atomicAdd(&sh[k & 255u], 1u);
+      atomicAdd(&sh[256 + ((k >> 8) & 255u)], 1u);
+      atomicAdd(&sh[512 + ((k >> 16) & 255u)], 1u);
+      atomicAdd(&sh[768 + (k >> 24)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 1024; i += 256) {
+    uint32_t c = sh[i];
+    if (c) atomicAdd(&ghist[i], c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CSCalcViewData
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_splat_cut(const FrameConsts &fc, const GsCutout *__restrict__ cut, float3 p) {
+  // S/SplatUtilities.compute:164-187
+  bool finalCut = false;
+  for (uint32_t i = 0; i < fc.cutoutCount; ++i) {
+    const GsCutout &c = cut[i];
+    uint32_t type = c.type_and_flags & 0xFFu;
+    if (type == 0xFFu) continue;
+    bool invert = (c.type_and_flags & 0xFF00u) != 0;
+    const float *m = c.mat;  // column-major
+    float cx = fmaf(m[8], p.z, fmaf(m[4], p.y, fmaf(m[0], p.x, m[12])));
+    float cy = fmaf(m[9], p.z, fmaf(m[5], p.y, fmaf(m[1], p.x, m[13])));
+    float cz = fmaf(m[10], p.z, fmaf(m[6], p.y, fmaf(m[2], p.x, m[14])));
+    if (type == 0) { if (cx * cx + cy * cy + cz * cz <= 1.0f) return invert; }
+    if (type == 1) { if (fabsf(cx) <= 1.0f && fabsf(cy) <= 1.0f && fabsf(cz) <= 1.0f) return invert; }
+    finalCut |= !invert;
+  }
+  return finalCut;
+}
+
+// Raw SH words of one splat, loaded with 16-byte vector loads (strides 32/60/96/192 keep
+// at least 4-byte alignment; 60 is only 4-aligned so Norm11 uses word loads).
+template <int FMT>
+struct ShRaw;
+template <>
+struct ShRaw<3> {  // Norm6: 15 x u16 + pad = 32 B
+  uint32_t w[8];
+  __device__ __forceinline__ void load(const uint8_t *p) {
+    uint4 a = __ldg(reinterpret_cast<const uint4 *>(p)), b = __ldg(reinterpret_cast<const uint4 *>(p + 16));
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  }
+  __device__ __forceinline__ float3 get(int j) const { return dec_5_6_5((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu); }
+};
+template <>
+struct ShRaw<2> {  // Norm11: 15 x u32 = 60 B
+  uint32_t w[15];
+  __device__ __forceinline__ void load(const uint8_t *p) {
+#pragma unroll
+    for (int j = 0; j < 15; ++j) w[j] = __ldg(reinterpret_cast<const uint32_t *>(p) + j);
+  }
+  __device__ __forceinline__ float3 get(int j) const { return dec_11_10_11(w[j]); }
+};
+template <>
+struct ShRaw<1> {  // Float16: 45 halfs + pad = 96 B
+  uint32_t w[24];
+  __device__ __forceinline__ void load(const uint8_t *p) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      uint4 a = __ldg(reinterpret_cast<const uint4 *>(p) + q);
+      w[q * 4] = a.x; w[q * 4 + 1] = a.y; w[q * 4 + 2] = a.z; w[q * 4 + 3] = a.w;
+    }
+  }
+  __device__ __forceinline__ float h(int k) const { return (k & 1) ? f16hi(w[k >> 1]) : f16lo(w[k >> 1]); }
+  __device__ __forceinline__ float3 get(int j) const { return make_float3(h(j * 3), h(j * 3 + 1), h(j * 3 + 2)); }
+};
+template <>
+struct ShRaw<0> {  // Float32: 45 floats + pad = 192 B
+  uint32_t w[48];
+  __device__ __forceinline__ void load(const uint8_t *p) {
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+      uint4 a = __ldg(reinterpret_cast<const uint4 *>(p) + q);
+      w[q * 4] = a.x; w[q * 4 + 1] = a.y; w[q * 4 + 2] = a.z; w[q * 4 + 3] = a.w;
+    }
+  }
+  __device__ __forceinline__ float3 get(int j) const {
+    return make_float3(__uint_as_float(w[j * 3]), __uint_as_float(w[j * 3 + 1]), __uint_as_float(w[j * 3 + 2]));
+  }
+};
+
+__device__ __forceinline__ float3 operator*(float s, float3 v) { return make_float3(s * v.x, s * v.y, s * v.z); }
+__device__ __forceinline__ float3 operator*(float3 v, float s) { return make_float3(v.x * s, v.y * s, v.z * s); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 neg(float3 a) { return make_float3(-a.x, -a.y, -a.z); }
+
+template <int SHFMT>
+__global__ void __launch_bounds__(256)
+k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
+            uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out) {
+  __shared__ __align__(16) uint32_t s_view[256 * 10];
+  __shared__ __align__(16) Chunk s_chunk;
+  const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
+  const bool chunked = blockIdx.x < a.chunkCount;
+  if (chunked && threadIdx.x < 4)
+    reinterpret_cast<uint4 *>(&s_chunk)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(a.chunks + blockIdx.x) + threadIdx.x);
+  __syncthreads();
+
+  uint32_t vw[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) vw[k] = 0;
+  uint32_t rect = kRectEmpty;
+
+  if (idx < a.n) {
+    // ---- LoadSplatData, S/GaussianSplatting.hlsl:428-608 ----
+    const uint32_t otherStride = 4 + vec_stride(a.scaleFmt);
+    const uint64_t otherAddr = (uint64_t)idx * otherStride;
+    float3 pos = load_vector(a.pos, (uint64_t)idx * vec_stride(a.posFmt), a.posFmt);
+    uint32_t rq;
+    float3 scale;
+    if (a.scaleFmt == 2) {  // 8-byte record: one aligned 64-bit load
+      uint2 o = __ldg(reinterpret_cast<const uint2 *>(a.other + otherAddr));
+      rq = o.x;
+      scale = dec_11_10_11(o.y);
+    } else if (a.scaleFmt == 0) {  // 16-byte record
+      uint4 o = __ldg(reinterpret_cast<const uint4 *>(a.other + otherAddr));
+      rq = o.x;
+      scale = make_float3(__uint_as_float(o.y), __uint_as_float(o.z), __uint_as_float(o.w));
+    } else {
+      rq = (otherAddr & 3) == 0 ? ld_u32(a.other + otherAddr) : ld_u32_a2(a.other + otherAddr);
+      scale = load_vector(a.other, otherAddr + 4, a.scaleFmt);
+    }
+    // DecodeRotation(DecodePacked_10_10_10_2), :219-229,:293-300
+    float4 rot;
+    {
+      float px = (float)(rq & 1023) * GS_INV(1023.0f), py = (float)((rq >> 10) & 1023) * GS_INV(1023.0f),
+            pz = (float)((rq >> 20) & 1023) * GS_INV(1023.0f);
+      uint32_t qi = rq >> 30;  // round(w/3*3)
+      const float kSqrt2 = 1.41421354f, kInvSqrt2 = 0.707106769f;
+      float x = fmaf(px, kSqrt2, -kInvSqrt2), y = fmaf(py, kSqrt2, -kInvSqrt2), z = fmaf(pz, kSqrt2, -kInvSqrt2);
+      float w = sqrtf(1.0f - satf(fmaf(z, z, fmaf(y, y, x * x))));
+      rot = make_float4(x, y, z, w);
+      if (qi == 0) rot = make_float4(w, x, y, z);
+      if (qi == 1) rot = make_float4(x, w, y, z);
+      if (qi == 2) rot = make_float4(x, y, w, z);
+    }
+    // colour texel (Morton-swizzled 2048-wide image), :423-426
+    float4 col;
+    {
+      const uint32_t ti = splat_index_to_texel(idx);
+      if (a.colFmt == 0) {
+        col = __ldg(reinterpret_cast<const float4 *>(a.color) + ti);
+      } else if (a.colFmt == 1) {
+        uint2 e = __ldg(reinterpret_cast<const uint2 *>(a.color) + ti);
+        col = make_float4(f16lo(e.x), f16hi(e.x), f16lo(e.y), f16hi(e.y));
+      } else {
+        uint32_t e = __ldg(reinterpret_cast<const uint32_t *>(a.color) + ti);
+        col = make_float4(__fdiv_rn((float)(e & 255u), 255.0f), __fdiv_rn((float)((e >> 8) & 255u), 255.0f),
+                          __fdiv_rn((float)((e >> 16) & 255u), 255.0f), __fdiv_rn((float)(e >> 24), 255.0f));
+      }
+    }
+    ShRaw<SHFMT> shr;
+    constexpr uint32_t shStride = SHFMT == 0 ? 192u : SHFMT == 1 ? 96u : SHFMT == 2 ? 60u : 32u;
+    if (fc.shOrder >= 1) shr.load(a.sh + (uint64_t)idx * shStride);
+
+    float3 shMin = make_float3(0.f, 0.f, 0.f), shMax = make_float3(1.f, 1.f, 1.f);
+    if (chunked) {  // :565-603
+      pos.x = lerpf(s_chunk.posX.x, s_chunk.posX.y, pos.x);
+      pos.y = lerpf(s_chunk.posY.x, s_chunk.posY.y, pos.y);
+      pos.z = lerpf(s_chunk.posZ.x, s_chunk.posZ.y, pos.z);
+      scale.x = lerpf(f16lo(s_chunk.sclX), f16hi(s_chunk.sclX), scale.x);
+      scale.y = lerpf(f16lo(s_chunk.sclY), f16hi(s_chunk.sclY), scale.y);
+      scale.z = lerpf(f16lo(s_chunk.sclZ), f16hi(s_chunk.sclZ), scale.z);
+      scale.x *= scale.x; scale.x *= scale.x; scale.x *= scale.x;
+      scale.y *= scale.y; scale.y *= scale.y; scale.y *= scale.y;
+      scale.z *= scale.z; scale.z *= scale.z; scale.z *= scale.z;
+      col.x = lerpf(f16lo(s_chunk.colR), f16hi(s_chunk.colR), col.x);
+      col.y = lerpf(f16lo(s_chunk.colG), f16hi(s_chunk.colG), col.y);
+      col.z = lerpf(f16lo(s_chunk.colB), f16hi(s_chunk.colB), col.z);
+      col.w = lerpf(f16lo(s_chunk.colA), f16hi(s_chunk.colA), col.w);
+      {  // InvSquareCentered01, :5-11
+        float x = col.w - 0.5f;
+        x *= 0.5f;
+        float sg = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
+        col.w = sqrtf(fabsf(x)) * sg + 0.5f;
+      }
+      shMin = make_float3(f16lo(s_chunk.shR), f16lo(s_chunk.shG), f16lo(s_chunk.shB));
+      shMax = make_float3(f16hi(s_chunk.shR), f16hi(s_chunk.shG), f16hi(s_chunk.shB));
+    }
+    const bool shLerp = chunked && SHFMT != 0;  // shFormat > FLOAT32 && <= NORM6, :585
+    auto SH = [&](int j) -> float3 {
+      float3 v = shr.get(j - 1);
+      if (shLerp) { v.x = lerpf(shMin.x, shMax.x, v.x); v.y = lerpf(shMin.y, shMax.y, v.y); v.z = lerpf(shMin.z, shMax.z, v.z); }
+      return v;
+    };
+
+    // ---- CSCalcViewData body, S/SplatUtilities.compute:199-251 ----
+    float3 cw = make_float3(fmaf(fc.o2w[2], pos.z, fmaf(fc.o2w[1], pos.y, fmaf(fc.o2w[0], pos.x, fc.o2w[3]))),
+                            fmaf(fc.o2w[6], pos.z, fmaf(fc.o2w[5], pos.y, fmaf(fc.o2w[4], pos.x, fc.o2w[7]))),
+                            fmaf(fc.o2w[10], pos.z, fmaf(fc.o2w[9], pos.y, fmaf(fc.o2w[8], pos.x, fc.o2w[11]))));
+    float4 clip;
+    clip.x = fmaf(fc.vp[2], cw.z, fmaf(fc.vp[1], cw.y, fmaf(fc.vp[0], cw.x, fc.vp[3])));
+    clip.y = fmaf(fc.vp[6], cw.z, fmaf(fc.vp[5], cw.y, fmaf(fc.vp[4], cw.x, fc.vp[7])));
+    clip.z = fmaf(fc.vp[10], cw.z, fmaf(fc.vp[9], cw.y, fmaf(fc.vp[8], cw.x, fc.vp[11])));
+    clip.w = fmaf(fc.vp[14], cw.z, fmaf(fc.vp[13], cw.y, fmaf(fc.vp[12], cw.x, fc.vp[15])));
+    if (fc.bitsValid) {
+      if (__ldg(deleted + (idx >> 5)) & (1u << (idx & 31))) clip.w = 0.0f;
+    }
+    if (fc.cutoutCount && is_splat_cut(fc, cutouts, pos)) clip.w = 0.0f;
+    vw[0] = __float_as_uint(clip.x); vw[1] = __float_as_uint(clip.y); vw[2] = __float_as_uint(clip.z); vw[3] = __float_as_uint(clip.w);
+
+    if (!(clip.w <= 0.0f)) {
+      // CalcMatrixFromRotationScale, S/GaussianSplatting.hlsl:29-46
+      const float x = rot.x, y = rot.y, z = rot.z, w = rot.w;
+      float m[3][3];
+      m[0][0] = (1.0f - 2.0f * (y * y + z * z)) * scale.x; m[0][1] = (2.0f * (x * y - w * z)) * scale.y; m[0][2] = (2.0f * (x * z + w * y)) * scale.z;
+      m[1][0] = (2.0f * (x * y + w * z)) * scale.x; m[1][1] = (1.0f - 2.0f * (x * x + z * z)) * scale.y; m[1][2] = (2.0f * (y * z - w * x)) * scale.z;
+      m[2][0] = (2.0f * (x * z - w * y)) * scale.x; m[2][1] = (2.0f * (y * z + w * x)) * scale.y; m[2][2] = (1.0f - 2.0f * (x * x + y * y)) * scale.z;
+      // CalcCovariance3D :48-53 (* splatScale^2, S/SplatUtilities.compute:233-235)
+      float sig[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = r; c < 3; ++c) sig[r][c] = sig[c][r] = (m[r][0] * m[c][0] + m[r][1] * m[c][1] + m[r][2] * m[c][2]) * fc.splatScale2;
+      // CalcCovariance2D :56-90
+      float vx = fmaf(fc.mv[2], pos.z, fmaf(fc.mv[1], pos.y, fmaf(fc.mv[0], pos.x, fc.mv[3])));
+      float vy = fmaf(fc.mv[6], pos.z, fmaf(fc.mv[5], pos.y, fmaf(fc.mv[4], pos.x, fc.mv[7])));
+      float tz = fmaf(fc.mv[10], pos.z, fmaf(fc.mv[9], pos.y, fmaf(fc.mv[8], pos.x, fc.mv[11])));
+      float cxn = fminf(fmaxf(__fdiv_rn(vx, tz), -fc.limX), fc.limX), cyn = fminf(fmaxf(__fdiv_rn(vy, tz), -fc.limY), fc.limY);
+      float tx = cxn * tz, ty = cyn * tz;
+      float j00 = __fdiv_rn(fc.focal, tz), j02 = -__fdiv_rn(fc.focal * tx, tz * tz), j12 = -__fdiv_rn(fc.focal * ty, tz * tz);
+      float T[2][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        T[0][c] = j00 * fc.mv[c] + j02 * fc.mv[8 + c];
+        T[1][c] = j00 * fc.mv[4 + c] + j12 * fc.mv[8 + c];
+      }
+      float vt[3][2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) vt[k][i] = sig[k][0] * T[i][0] + sig[k][1] * T[i][1] + sig[k][2] * T[i][2];
+      float cov00 = T[0][0] * vt[0][0] + T[0][1] * vt[1][0] + T[0][2] * vt[2][0];
+      float cov01 = T[0][0] * vt[0][1] + T[0][1] * vt[1][1] + T[0][2] * vt[2][1];
+      float cov11 = T[1][0] * vt[0][1] + T[1][1] * vt[1][1] + T[1][2] * vt[2][1];
+      cov00 += 0.3f; cov11 += 0.3f;
+      // DecomposeCovariance, S/SplatUtilities.compute:149-159
+      float mid = 0.5f * (cov00 + cov11);
+      float hd = (cov00 - cov11) * 0.5f;
+      float radius = sqrtf(hd * hd + cov01 * cov01);
+      float lambda1 = mid + radius;
+      float lambda2 = fmaxf(mid - radius, 0.1f);
+      float dvx = cov01, dvy = lambda1 - cov00;
+      float dl = sqrtf(dvx * dvx + dvy * dvy);
+      dvx = __fdiv_rn(dvx, dl); dvy = __fdiv_rn(dvy, dl);
+      dvy = -dvy;
+      float l1 = fminf(sqrtf(2.0f * lambda1), 4096.0f), l2 = fminf(sqrtf(2.0f * lambda2), 4096.0f);
+      float a1x = l1 * dvx, a1y = l1 * dvy, a2x = l2 * dvy, a2y = l2 * -dvx;
+      vw[4] = __float_as_uint(a1x); vw[5] = __float_as_uint(a1y); vw[6] = __float_as_uint(a2x); vw[7] = __float_as_uint(a2y);
+      // colour: ShadeSH(objViewDir), :240-248 + S/GaussianSplatting.hlsl:139-179
+      float wx = fc.cam_pos[0] - cw.x, wy = fc.cam_pos[1] - cw.y, wz = fc.cam_pos[2] - cw.z;
+      float ox = fmaf(fc.w2o[2], wz, fmaf(fc.w2o[1], wy, fc.w2o[0] * wx));
+      float oy = fmaf(fc.w2o[5], wz, fmaf(fc.w2o[4], wy, fc.w2o[3] * wx));
+      float oz = fmaf(fc.w2o[8], wz, fmaf(fc.w2o[7], wy, fc.w2o[6] * wx));
+      float ol = sqrtf(ox * ox + oy * oy + oz * oz);
+      ox = __fdiv_rn(ox, ol); oy = __fdiv_rn(oy, ol); oz = __fdiv_rn(oz, ol);
+      const float dx = ox * -1.0f, dy = oy * -1.0f, dz = oz * -1.0f;  // dir *= -1
+      float3 res = fc.shOnly ? make_float3(0.5f, 0.5f, 0.5f) : make_float3(col.x, col.y, col.z);
+      if (fc.shOrder >= 1) {
+        const float SH_C1 = 0.4886025f;
+        res = res + SH_C1 * (neg(SH(1)) * dy + SH(2) * dz - SH(3) * dx);
+        if (fc.shOrder >= 2) {
+          const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+          res = res + ((1.0925484f * xy) * SH(4) + (-1.0925484f * yz) * SH(5) + (0.3153916f * (2.0f * zz - xx - yy)) * SH(6) +
+                       (-1.0925484f * xz) * SH(7) + (0.5462742f * (xx - yy)) * SH(8));
+          if (fc.shOrder >= 3) {
+            res = res + ((-0.5900436f * dy * (3.0f * xx - yy)) * SH(9) + (2.8906114f * xy * dz) * SH(10) +
+                         (-0.4570458f * dy * (4.0f * zz - xx - yy)) * SH(11) + (0.3731763f * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy)) * SH(12) +
+                         (-0.4570458f * dx * (4.0f * zz - xx - yy)) * SH(13) + (1.4453057f * dz * (xx - yy)) * SH(14) +
+                         (-0.5900436f * dx * (xx - 3.0f * yy)) * SH(15));
+          }
+        }
+      }
+      res.x = (res.x > 0.0f) ? res.x : 0.0f; res.y = (res.y > 0.0f) ? res.y : 0.0f; res.z = (res.z > 0.0f) ? res.z : 0.0f;
+      float alpha = fminf(col.w * fc.opacityScale, 65000.0f);
+      vw[8] = (f32tof16(res.x) << 16) | f32tof16(res.y);
+      vw[9] = (f32tof16(res.z) << 16) | f32tof16(alpha);
+      SplatFootprint fp;
+      if (splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp))
+        rect = footprint_tile_rect(fp, fc);
+    }
+    rect_out[idx] = rect;
+  }
+
+  // ---- coalesced store of the CTA's 256 x 40-byte records ----
+#pragma unroll
+  for (int k = 0; k < 10; ++k) s_view[threadIdx.x * 10 + k] = vw[k];
+  __syncthreads();
+  const uint32_t first = blockIdx.x * 256;
+  const uint32_t cnt = min(256u, a.n - first);
+  const uint32_t words = cnt * 10;
+  uint4 *dst = reinterpret_cast<uint4 *>(view_out + (uint64_t)first * 10);
+  const uint4 *src = reinterpret_cast<const uint4 *>(s_view);
+  for (uint32_t q = threadIdx.x; q * 4 + 3 < words; q += 256) dst[q] = src[q];
+  // tail words when cnt*10 is not a multiple of 4 (only the last CTA)
+  for (uint32_t wi = (words & ~3u) + threadIdx.x; wi < words; wi += 256) view_out[(uint64_t)first * 10 + wi] = s_view[wi];
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s) {
+  if (n) k_set_indices<<<(n + 255) / 256, 256, 0, s>>>(order, n);
+}
+
+void launch_calc_distances(const AssetView &a, const FrameConsts &fc, const uint32_t *order, uint32_t *keys, uint32_t *ghist,
+                           cudaStream_t s) {
+  if (!a.n) return;
+  const uint32_t per = 256 * kDistItems;
+  k_calc_distances<<<(a.n + per - 1) / per, 256, 0, s>>>(a, make_float4(fc.sort_row[0], fc.sort_row[1], fc.sort_row[2], fc.sort_row[3]),
+                                                         order, keys, ghist);
+}
+
+void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
+                      uint32_t *rect, cudaStream_t s) {
+  if (!a.n) return;
+  const uint32_t grid = (a.n + 255) / 256;
+  switch (a.shFmt) {
+    case 0: k_calc_view<0><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
+    case 1: k_calc_view<1><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
+    case 2: k_calc_view<2><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
+    default: k_calc_view<3><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
+  }
+}
+
+}  // namespace gs
