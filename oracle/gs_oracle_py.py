@@ -1,0 +1,152 @@
+"""ctypes binding of the CPU oracle (oracle/libgs_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs.  Never by the product package.  PARITY UNPINNED -- see gs_oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "libgs_oracle.so"
+
+
+class GsoAsset(C.Structure):
+    _fields_ = [("splat_count", C.c_uint32), ("pos_format", C.c_uint32), ("scale_format", C.c_uint32), ("sh_format", C.c_uint32),
+                ("color_format", C.c_uint32), ("pos", C.c_void_p), ("other", C.c_void_p), ("sh", C.c_void_p), ("color", C.c_void_p),
+                ("chunks", C.c_void_p), ("pos_bytes", C.c_uint64), ("other_bytes", C.c_uint64), ("sh_bytes", C.c_uint64),
+                ("color_bytes", C.c_uint64), ("chunk_bytes", C.c_uint64)]
+
+
+class GsoCutout(C.Structure):
+    _fields_ = [("mat", C.c_float * 16), ("type_and_flags", C.c_uint32)]
+
+
+class GsoFrame(C.Structure):
+    _fields_ = [("mat_object_to_world", C.c_float * 16), ("mat_world_to_object", C.c_float * 16), ("mat_view", C.c_float * 16),
+                ("mat_proj_gpu", C.c_float * 16), ("screen_w", C.c_float), ("screen_h", C.c_float), ("cam_pos_world", C.c_float * 3),
+                ("splat_scale", C.c_float), ("opacity_scale", C.c_float), ("sh_order", C.c_uint32), ("sh_only", C.c_uint32),
+                ("cutout_count", C.c_uint32), ("reserved0", C.c_uint32), ("cutouts", C.c_void_p), ("deleted_bits", C.c_void_p)]
+
+
+class GsoSplat(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("rot", C.c_float * 4), ("scale", C.c_float * 3), ("opacity", C.c_float),
+                ("col", C.c_float * 3), ("sh", C.c_float * 45)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB.exists():
+            subprocess.run(["make", "-C", str(HERE)], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        L = C.CDLL(str(LIB))
+        L.gso_f32tof16.restype, L.gso_f32tof16.argtypes = C.c_uint32, [C.c_float]
+        L.gso_f16tof32.restype, L.gso_f16tof32.argtypes = C.c_float, [C.c_uint32]
+        L.gso_exp_neg.restype, L.gso_exp_neg.argtypes = C.c_float, [C.c_float]
+        L.gso_float_to_sortable_uint.restype, L.gso_float_to_sortable_uint.argtypes = C.c_uint32, [C.c_float]
+        L.gso_inv_square_centered01.restype, L.gso_inv_square_centered01.argtypes = C.c_float, [C.c_float]
+        L.gso_splat_index_to_pixel_index.restype = C.c_uint32
+        L.gso_splat_index_to_pixel_index.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.gso_load_splat_pos.restype, L.gso_load_splat_pos.argtypes = None, [C.POINTER(GsoAsset), C.c_uint32, C.c_void_p]
+        L.gso_load_splat_data.restype, L.gso_load_splat_data.argtypes = None, [C.POINTER(GsoAsset), C.c_uint32, C.POINTER(GsoSplat)]
+        L.gso_set_indices.restype, L.gso_set_indices.argtypes = None, [C.c_void_p, C.c_uint32]
+        L.gso_calc_distances.restype = None
+        L.gso_calc_distances.argtypes = [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_void_p, C.c_void_p, C.c_int]
+        L.gso_sort_pairs.restype, L.gso_sort_pairs.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+        L.gso_calc_view.restype, L.gso_calc_view.argtypes = None, [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_void_p, C.c_int]
+        L.gso_render.restype = None
+        L.gso_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
+        L.gso_composite.restype, L.gso_composite.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        L.gso_max_threads.restype, L.gso_max_threads.argtypes = C.c_int, []
+        _lib = L
+    return _lib
+
+
+def max_threads() -> int:
+    return int(lib().gso_max_threads())
+
+
+def asset_struct(asset) -> GsoAsset:
+    """asset: unitygaussiansplatting_b200.asset.GaussianSplatAsset (numpy blobs, borrowed)."""
+    a = GsoAsset()
+    a.splat_count = asset.splatCount
+    a.pos_format, a.scale_format = int(asset.posFormat), int(asset.scaleFormat)
+    a.sh_format, a.color_format = int(asset.shFormat), int(asset.colorFormat)
+    a.pos, a.pos_bytes = asset.posData.ctypes.data, asset.posData.nbytes
+    a.other, a.other_bytes = asset.otherData.ctypes.data, asset.otherData.nbytes
+    a.sh, a.sh_bytes = asset.shData.ctypes.data, asset.shData.nbytes
+    a.color, a.color_bytes = asset.colorData.ctypes.data, asset.colorData.nbytes
+    if asset.chunkData is not None and asset.chunkData.nbytes:
+        a.chunks, a.chunk_bytes = asset.chunkData.ctypes.data, asset.chunkData.nbytes
+    else:
+        a.chunks, a.chunk_bytes = None, 0
+    return a
+
+
+def frame_struct(fp) -> GsoFrame:
+    """fp: the product's GsFrameParams (same field layout); copied byte for byte."""
+    f = GsoFrame()
+    assert C.sizeof(f) == C.sizeof(fp)
+    C.memmove(C.byref(f), C.byref(fp), C.sizeof(f))
+    return f
+
+
+def load_splat(asset, idx: int) -> dict:
+    a, s = asset_struct(asset), GsoSplat()
+    lib().gso_load_splat_data(C.byref(a), idx, C.byref(s))
+    return {"pos": np.array(s.pos[:], np.float32), "rot": np.array(s.rot[:], np.float32), "scale": np.array(s.scale[:], np.float32),
+            "opacity": np.float32(s.opacity), "col": np.array(s.col[:], np.float32), "sh": np.array(s.sh[:], np.float32).reshape(15, 3)}
+
+
+def calc_distances(asset, fp, order: np.ndarray, threads: int = 1) -> np.ndarray:
+    a, f = asset_struct(asset), frame_struct(fp)
+    order = np.ascontiguousarray(order, np.uint32)
+    keys = np.empty(asset.splatCount, np.uint32)
+    lib().gso_calc_distances(C.byref(a), C.byref(f), order.ctypes.data, keys.ctypes.data, threads)
+    return keys
+
+
+def sort_pairs(keys: np.ndarray, payload: np.ndarray, threads: int = 1):
+    assert keys.dtype == np.uint32 and payload.dtype == np.uint32 and keys.flags.c_contiguous and payload.flags.c_contiguous
+    lib().gso_sort_pairs(keys.ctypes.data, payload.ctypes.data, keys.size, threads)
+
+
+def calc_view(asset, fp, threads: int = 1) -> np.ndarray:
+    a, f = asset_struct(asset), frame_struct(fp)
+    view = np.zeros((asset.splatCount, 10), np.uint32)
+    lib().gso_calc_view(C.byref(a), C.byref(f), view.ctypes.data, threads)
+    return view
+
+
+def render(view: np.ndarray, order: np.ndarray, width: int, height: int, blend_mode: int = 0, threads: int = 1) -> np.ndarray:
+    view = np.ascontiguousarray(view, np.uint32)
+    order = np.ascontiguousarray(order, np.uint32)
+    rt = np.zeros((height, width, 4), np.float32)
+    lib().gso_render(view.ctypes.data, order.ctypes.data, order.size, width, height, blend_mode, rt.ctypes.data, threads)
+    return rt
+
+
+def composite(rt: np.ndarray, target: np.ndarray, target_fp16: bool = False) -> np.ndarray:
+    rt = np.ascontiguousarray(rt, np.float32)
+    out = np.ascontiguousarray(target, np.float32).copy()
+    lib().gso_composite(rt.ctypes.data, out.ctypes.data, rt.shape[1], rt.shape[0], 1 if target_fp16 else 0)
+    return out
+
+
+def frame(asset, fp, prev_order=None, width=None, height=None, blend_mode: int = 0, threads: int = 1):
+    """Whole path: distances -> stable sort -> view -> draw.  Returns dict of every intermediate."""
+    n = asset.splatCount
+    order = np.arange(n, dtype=np.uint32) if prev_order is None else np.ascontiguousarray(prev_order, np.uint32).copy()
+    keys = calc_distances(asset, fp, order, threads)
+    sort_pairs(keys, order, threads)
+    view = calc_view(asset, fp, threads)
+    W, H = int(width or fp.screen_w), int(height or fp.screen_h)
+    rt = render(view, order, W, H, blend_mode, threads)
+    return {"keys": keys, "order": order, "view": view, "rt": rt}

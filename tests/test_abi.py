@@ -1,0 +1,60 @@
+"""The C-ABI library loads and exports every symbol the headers declare (no compute without a GPU)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+from conftest import has_cuda
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared(header: str, prefix: str):
+    text = (ROOT / "include" / header).read_text()
+    return sorted(set(re.findall(r"\b(%s[a-z0-9_]+)\s*\(" % prefix, text)))
+
+
+def test_native_exports_every_declared_symbol(g):
+    from unitygaussiansplatting_b200 import _native as N
+    lib = N.native()
+    declared = _declared("gsplat_b200.h", "gs_")
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libgsplat_b200.so does not export %s" % name
+    assert set(declared) == set(N.NATIVE_SYMBOLS), "python binding table out of sync with the header"
+    assert b"sm_100a" in lib.gs_version()
+
+
+def test_asset_lib_exports_every_declared_symbol(g):
+    from unitygaussiansplatting_b200 import _native as N
+    lib = N.asset_lib()
+    declared = _declared("gsplat_asset.h", "gsa_")
+    for name in declared:
+        assert hasattr(lib, name)
+    assert set(declared) == set(N.ASSET_SYMBOLS)
+
+
+def test_struct_layouts_match_the_header():
+    from unitygaussiansplatting_b200 import _native as N
+    assert C.sizeof(N.GsCutout) == 68                      # R/GaussianCutout.cs:20-24
+    assert C.sizeof(N.GsAssetDesc) == 4 * 5 + 4 + 8 * 5 + 8 * 5
+    assert C.sizeof(N.GsFrameParams) == 64 * 4 + 8 + 12 + 8 + 8 + 8 + 4 + 16
+    assert C.sizeof(N.GsImage) == 32
+    assert C.sizeof(N.GsRenderOptions) == 24
+
+
+@pytest.mark.skipif(has_cuda(), reason="CPU-only behaviour")
+def test_no_cpu_fallback(g):
+    """Without a device the product fails loudly instead of falling back to anything."""
+    with pytest.raises(g.GsError) as e:
+        g.GaussianSplatContext(0)
+    assert e.value.code == -6
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / "unitygaussiansplatting_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.cpp")):
+        text = p.read_text()
+        for needle in ("gs_oracle", "import oracle", "from oracle", "gso_", "oracle/gs", "oracle\" /"):
+            assert needle not in text, "%s references the oracle (%s)" % (p, needle)

@@ -1,0 +1,163 @@
+"""GPU parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+Bar: bit-exact keys / order / SplatViewData; render target within 1e-3 per channel (it is in fact
+bit-exact in GS_BLEND_FP16_ROP mode because both sides share one arithmetic contract)."""
+import numpy as np
+import pytest
+
+from util import camera, lattice_camera, one_splat
+
+pytestmark = pytest.mark.gpu
+
+RT_TOL = 1e-3  # BASELINE.json north_star: pixels within 1e-3 per channel
+
+
+def _frame_pair(g, O, ctx, asset, cam, blend=0, prev_order=None, **knobs):
+    r = g.GaussianSplatRenderer(asset, ctx)
+    for k, v in knobs.items():
+        setattr(r, k, v)
+    r.blend_mode = blend
+    if prev_order is not None:
+        r.upload_order(prev_order)
+    rt = np.zeros((cam.pixelHeight, cam.pixelWidth, 4), np.float32 if blend == 1 else np.float16)
+    r.SortAndRenderSplats(cam, rt=rt)
+    fp, _keep = g.make_frame_params(cam, r.localToWorldMatrix, r.m_SplatScale, r.m_OpacityScale, r.m_SHOrder, r.m_SHOnly,
+                                    r.m_Cutouts, r.m_DeletedBits, asset.splatCount)
+    ref = O.frame(asset, fp, prev_order=prev_order, blend_mode=blend, threads=O.max_threads())
+    got = {"keys": r.readback_keys(), "order": r.readback_order(), "view": r.readback_view(), "rt": rt.astype(np.float32)}
+    r.Dispose()
+    return got, ref
+
+
+def _assert_frame(got, ref, exact_rt=True):
+    assert np.array_equal(got["keys"], ref["keys"]), "sorted distance keys differ"
+    assert np.array_equal(got["order"], ref["order"]), "sorted splat indices differ"
+    bad = np.nonzero((got["view"] != ref["view"]).any(axis=1))[0]
+    assert bad.size == 0, "SplatViewData differs for %d splats, first %s" % (bad.size, bad[:5])
+    err = np.abs(got["rt"] - ref["rt"])
+    assert np.nanmax(err) <= RT_TOL, "render target max err %g at %s" % (err.max(), np.unravel_index(err.argmax(), err.shape))
+    assert not np.isnan(got["rt"]).any()
+    if exact_rt:
+        assert np.array_equal(got["rt"], ref["rt"]), "fp16-ROP render target is expected to be bit-exact (max err %g)" % err.max()
+
+
+@pytest.mark.parametrize("quality", ["Medium", "VeryHigh", "High"])
+def test_cfg1_lattice_1k(g, O, ctx, quality):
+    """BASELINE configs[0]: 1k axis-aligned gaussians with deliberate depth ties."""
+    asset = g.synthetic_asset(g.SCENE_LATTICE, 1000, 0x5EED0001, quality)
+    got, ref = _frame_pair(g, O, ctx, asset, lattice_camera(g, 256, 256))
+    assert (np.diff(ref["keys"].astype(np.int64)) == 0).sum() > 10, "the fixture is supposed to contain depth ties"
+    _assert_frame(got, ref)
+
+
+@pytest.mark.parametrize("quality,n,w,h", [("Medium", 50000, 400, 300), ("VeryHigh", 30000, 320, 180), ("High", 30000, 333, 211)])
+def test_clustered_scene(g, O, ctx, quality, n, w, h):
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, n, 0x5EED0002, quality)
+    got, ref = _frame_pair(g, O, ctx, asset, camera(g, w, h))
+    _assert_frame(got, ref)
+
+
+def test_fp32_blend_mode(g, O, ctx):
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 40000, 0x5EED0002, "Medium")
+    got, ref = _frame_pair(g, O, ctx, asset, camera(g, 320, 240), blend=1)
+    _assert_frame(got, ref, exact_rt=True)
+
+
+def test_tie_order_follows_previous_frame(g, O, ctx):
+    """CSCalcDistances gathers through the previous order and the sort is stable (SURVEY 7 'Tie order')."""
+    asset = g.synthetic_asset(g.SCENE_LATTICE, 1000, 0x5EED0001, "Medium")
+    rng = np.random.default_rng(5)
+    prev = rng.permutation(1000).astype(np.uint32)
+    got, ref = _frame_pair(g, O, ctx, asset, lattice_camera(g, 128, 128), prev_order=prev)
+    _assert_frame(got, ref)
+    got2, ref2 = _frame_pair(g, O, ctx, asset, lattice_camera(g, 128, 128))
+    assert not np.array_equal(ref["order"], ref2["order"]), "ties must resolve differently for a different history"
+
+
+def test_second_frame_reuses_order(g, O, ctx):
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 20000, 0x5EED0003, "Medium")
+    r = g.GaussianSplatRenderer(asset, ctx)
+    cams = [camera(g, 200, 150), camera(g, 200, 150, pos=(2.0, 1.0, -5.0), forward=(-0.3, -0.1, 1.0))]
+    order = np.arange(asset.splatCount, dtype=np.uint32)
+    for cam in cams:
+        rt = np.zeros((150, 200, 4), np.float16)
+        r.SortAndRenderSplats(cam, rt=rt)
+        fp, _k = g.make_frame_params(cam)
+        ref = O.frame(asset, fp, prev_order=order, threads=O.max_threads())
+        order = ref["order"]
+        assert np.array_equal(r.readback_order(), order)
+        assert np.array_equal(rt.astype(np.float32), ref["rt"])
+    r.Dispose()
+
+
+@pytest.mark.parametrize("knobs", [dict(m_SHOrder=0), dict(m_SHOrder=1), dict(m_SHOrder=2), dict(m_SHOnly=True),
+                                   dict(m_SplatScale=0.5, m_OpacityScale=3.0), dict(m_SplatScale=2.0, m_OpacityScale=0.2)])
+def test_render_knobs(g, O, ctx, knobs):
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 20000, 0x5EED0004, "Medium")
+    got, ref = _frame_pair(g, O, ctx, asset, camera(g, 256, 160), **knobs)
+    _assert_frame(got, ref)
+
+
+def test_object_transform_cutouts_and_deleted_bits(g, O, ctx):
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 20000, 0x5EED0005, "Medium")
+    # GSTestScene.unity:363-365: rotation quaternion (-0.9925,0,0,0.1219), scale (1,1,-1)
+    o2w = g.trs((0.3, -0.2, 0.5), g.quat_to_mat((-0.9925, 0.0, 0.0, 0.1219)), (1, 1, -1)).astype(np.float32)
+    cut_e = (g.trs((0, 0, 0), None, (0.25, 0.25, 0.25)).astype(np.float32), 0)            # ellipsoid of radius 4
+    cut_b = (g.trs((0, 0, 0), None, (0.5, 0.5, 0.5)).astype(np.float32), 1 | 0x100)       # inverted box
+    bits = np.random.default_rng(3).integers(0, 2**32, (asset.splatCount + 31) // 32, dtype=np.uint32)
+    got, ref = _frame_pair(g, O, ctx, asset, camera(g, 256, 160), localToWorldMatrix=o2w, m_Cutouts=[cut_e, cut_b, (np.eye(4), 0xFFFFFFFF)],
+                           m_DeletedBits=bits)
+    _assert_frame(got, ref)
+    assert (got["view"][:, 3].view(np.float32) == 0).mean() > 0.3
+
+
+def test_single_huge_and_degenerate_splats(g, O, ctx):
+    cam = camera(g, 200, 120, pos=(0, 0, -3))
+    for kw in (dict(scale=(3.0, 3.0, 3.0)), dict(scale=(1e-4, 1e-4, 1e-4)), dict(pos=(0, 0, -10.0)), dict(opacity=0.003),
+               dict(scale=(2.0, 0.001, 0.001), quat=(0.1, 0.5, 0.3, 0.8))):
+        asset = one_splat(g, n_pad=3, **kw)
+        got, ref = _frame_pair(g, O, ctx, asset, cam)
+        _assert_frame(got, ref)
+
+
+def test_composite_matches_oracle(g, O, ctx):
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 20000, 0x5EED0002, "Medium")
+    cam = camera(g, 320, 200)
+    r = g.GaussianSplatRenderer(asset, ctx)
+    rng = np.random.default_rng(1)
+    bg = rng.random((200, 320, 4), np.float32)
+    for dt in (np.float32, np.float16):
+        rt = np.zeros((200, 320, 4), np.float16)
+        tgt = bg.astype(dt).copy()
+        r.m_FrameCounter = 0
+        r.SortAndRenderSplats(cam, rt=rt, camera_target=tgt)
+        want = O.composite(rt.astype(np.float32), bg.astype(dt).astype(np.float32), target_fp16=(dt == np.float16))
+        assert np.array_equal(tgt.astype(np.float32), want)
+        # stand-alone gs_composite on host images
+        tgt2 = bg.astype(dt).copy()
+        r.Composite(rt, tgt2)
+        assert np.array_equal(tgt2, tgt)
+    r.Dispose()
+
+
+def test_staged_calls_equal_fused_frame(g, O, ctx):
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 30000, 0x5EED0006, "Medium")
+    cam = camera(g, 300, 200)
+    a, b = g.GaussianSplatRenderer(asset, ctx), g.GaussianSplatRenderer(asset, ctx)
+    rt_a, rt_b = np.zeros((200, 300, 4), np.float16), np.zeros((200, 300, 4), np.float16)
+    a.SortAndRenderSplats(cam, rt=rt_a)
+    b.SortPoints(cam); b.CalcViewData(cam); b.DrawSplats(cam, rt_b)
+    assert np.array_equal(rt_a, rt_b) and np.array_equal(a.readback_order(), b.readback_order())
+    a.Dispose(); b.Dispose()
+
+
+def test_error_behaviour(g, ctx):
+    asset = g.synthetic_asset(g.SCENE_LATTICE, 1000, 1, "Medium")
+    r = g.GaussianSplatRenderer(asset, ctx)
+    cam = camera(g, 64, 64)
+    with pytest.raises(g.GsError) as e:      # DrawSplats before CalcViewData -> GS_ERR_NOT_READY, nothing crashes
+        r.DrawSplats(cam, np.zeros((64, 64, 4), np.float16))
+    assert e.value.code == -5
+    with pytest.raises(g.GsError):
+        r.m_SHOrder = 7
+        r.CalcViewData(cam)
+    r.Dispose()

@@ -1,0 +1,127 @@
+"""Host-side mirror of GaussianSplatAsset (package/Runtime/GaussianSplatAsset.cs) and of the
+importer's quality presets (package/Editor/GaussianSplatAssetCreator.cs:189-228).
+
+The byte blobs are produced by libgsplat_asset.so (csrc/asset_creator.cpp), which follows the
+reference importer's packing bit for bit; this module only owns the numpy buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from enum import IntEnum
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+
+
+class VectorFormat(IntEnum):  # R/GaussianSplatAsset.cs:31-37
+    Float32 = 0
+    Norm16 = 1
+    Norm11 = 2
+    Norm6 = 3
+
+
+class ColorFormat(IntEnum):  # R/GaussianSplatAsset.cs:51-57
+    Float32x4 = 0
+    Float16x4 = 1
+    Norm8x4 = 2
+    BC7 = 3
+
+
+class SHFormat(IntEnum):  # R/GaussianSplatAsset.cs:70-81
+    Float32 = 0
+    Float16 = 1
+    Norm11 = 2
+    Norm6 = 3
+    Cluster64k = 4
+    Cluster32k = 5
+    Cluster16k = 6
+    Cluster8k = 7
+    Cluster4k = 8
+
+
+# E/GaussianSplatAssetCreator.cs:195-224 -- presets the native path can decode (no BC7 / clustered SH)
+QUALITY = {
+    "Medium": (VectorFormat.Norm11, VectorFormat.Norm11, ColorFormat.Norm8x4, SHFormat.Norm6),
+    "High": (VectorFormat.Norm16, VectorFormat.Norm16, ColorFormat.Float16x4, SHFormat.Norm11),
+    "VeryHigh": (VectorFormat.Float32, VectorFormat.Float32, ColorFormat.Float32x4, SHFormat.Float32),
+}
+
+SCENE_LATTICE, SCENE_CLUSTERED, SCENE_UNIFORM = 0, 1, 2
+INPUT_SPLAT_FLOATS = 62  # InputSplatData, E/Utils/GaussianFileReader.cs:17-26
+
+
+@dataclass
+class GaussianSplatAsset:
+    splatCount: int
+    posFormat: VectorFormat
+    scaleFormat: VectorFormat
+    colorFormat: ColorFormat
+    shFormat: SHFormat
+    posData: np.ndarray
+    otherData: np.ndarray
+    colorData: np.ndarray
+    shData: np.ndarray
+    chunkData: Optional[np.ndarray]
+    boundsMin: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
+    boundsMax: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
+
+    @property
+    def total_bytes(self) -> int:
+        return sum(a.nbytes for a in (self.posData, self.otherData, self.colorData, self.shData) if a is not None) + (
+            self.chunkData.nbytes if self.chunkData is not None else 0)
+
+    def desc(self) -> N.GsAssetDesc:
+        d = N.GsAssetDesc()
+        d.splat_count = self.splatCount
+        d.pos_format, d.scale_format = int(self.posFormat), int(self.scaleFormat)
+        d.sh_format, d.color_format = int(self.shFormat), int(self.colorFormat)
+        d.pos, d.pos_bytes = self.posData.ctypes.data, self.posData.nbytes
+        d.other, d.other_bytes = self.otherData.ctypes.data, self.otherData.nbytes
+        d.sh, d.sh_bytes = self.shData.ctypes.data, self.shData.nbytes
+        d.color, d.color_bytes = self.colorData.ctypes.data, self.colorData.nbytes
+        if self.chunkData is not None and self.chunkData.nbytes:
+            d.chunks, d.chunk_bytes = self.chunkData.ctypes.data, self.chunkData.nbytes
+        else:
+            d.chunks, d.chunk_bytes = None, 0
+        return d
+
+
+def generate_input_splats(kind: int, n: int, seed: int) -> np.ndarray:
+    """Deterministic synthetic InputSplatData records (n x 62 float32), SURVEY.md 8d."""
+    out = np.empty((n, INPUT_SPLAT_FLOATS), np.float32)
+    rc = N.asset_lib().gsa_generate(kind, n, seed & 0xFFFFFFFF, out.ctypes.data)
+    if rc != 0:
+        raise ValueError("gsa_generate failed (%d)" % rc)
+    return out
+
+
+def create_asset(splats: np.ndarray, quality: str = "Medium", formats=None) -> GaussianSplatAsset:
+    """CreateAsset: Morton reorder, chunking, packing.  `splats` (n x 62 float32) is consumed."""
+    pf, sf, cf, shf = formats if formats is not None else QUALITY[quality]
+    if not (splats.dtype == np.float32 and splats.ndim == 2 and splats.shape[1] == INPUT_SPLAT_FLOATS and splats.flags.c_contiguous):
+        raise ValueError("splats must be a C-contiguous (n, 62) float32 array")
+    n = splats.shape[0]
+    lib = N.asset_lib()
+    sz = N.GsaSizes()
+    if lib.gsa_calc_sizes(n, int(pf), int(sf), int(cf), int(shf), C.byref(sz)) != 0:
+        raise ValueError("unsupported format combination (BC7 / clustered SH are out of scope)")
+    pos = np.zeros(sz.pos_bytes, np.uint8)
+    other = np.zeros(sz.other_bytes, np.uint8)
+    color = np.zeros(sz.color_bytes, np.uint8)
+    sh = np.zeros(sz.sh_bytes, np.uint8)
+    chunks = np.zeros(sz.chunk_bytes, np.uint8) if sz.chunk_bytes else None
+    bounds = np.zeros(6, np.float32)
+    rc = lib.gsa_create_asset(splats.ctypes.data, n, int(pf), int(sf), int(cf), int(shf), pos.ctypes.data, other.ctypes.data,
+                              color.ctypes.data, sh.ctypes.data, chunks.ctypes.data if chunks is not None else None,
+                              bounds.ctypes.data)
+    if rc != 0:
+        raise ValueError("gsa_create_asset failed (%d)" % rc)
+    return GaussianSplatAsset(n, VectorFormat(pf), VectorFormat(sf), ColorFormat(cf), SHFormat(shf), pos, other, color, sh, chunks,
+                              bounds[:3].copy(), bounds[3:].copy())
+
+
+def synthetic_asset(kind: int, n: int, seed: int, quality: str = "Medium") -> GaussianSplatAsset:
+    return create_asset(generate_input_splats(kind, n, seed), quality)

@@ -1,8 +1,10 @@
-"""In-tree native build of the three shared libraries.
+"""In-tree native build of the two product libraries.
 
   libgsplat_b200.so   CUDA hot path + C ABI (include/gsplat_b200.h), sm_100a only
   libgsplat_asset.so  host-side asset packer / synthetic scenes (include/gsplat_asset.h)
-  oracle/libgs_oracle.so  CPU oracle -- test infrastructure, built by its own Makefile
+
+(The CPU checker under the repo's test-infrastructure directory has its own Makefile and is
+built by __graft_entry__.build() / the test session, never from here.)
 
 Everything is compiled by explicit nvcc / g++ command lines (no JIT cache), so the
 artefacts travel with the tree to the GPU box.
@@ -20,8 +22,6 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 NATIVE_LIB = PKG / "libgsplat_b200.so"
 ASSET_LIB = PKG / "libgsplat_asset.so"
-ORACLE_DIR = ROOT / "oracle"
-ORACLE_LIB = ORACLE_DIR / "libgs_oracle.so"
 
 CU_SOURCES = ["gs_api.cu", "gs_view.cu", "gs_sort.cu", "gs_raster.cu"]
 CU_HEADERS = ["gs_common.cuh", "gs_kernels.cuh", "../../include/gsplat_b200.h"]
@@ -85,17 +85,10 @@ def build_asset(force: bool = False) -> Path:
     return ASSET_LIB
 
 
-def build_oracle(force: bool = False) -> Path:
-    if force and ORACLE_LIB.exists():
-        ORACLE_LIB.unlink()
-    _run(["make", "-C", str(ORACLE_DIR)])
-    return ORACLE_LIB
-
-
 def build_all(force: bool = False, verbose: bool = False):
-    return build_native(force, verbose), build_asset(force), build_oracle(force)
+    return build_native(force, verbose), build_asset(force)
 
 
 if __name__ == "__main__":
     build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print("built:", NATIVE_LIB, ASSET_LIB, ORACLE_LIB)
+    print("built:", NATIVE_LIB, ASSET_LIB)

@@ -1,0 +1,235 @@
+"""Host-side mirror of GaussianSplatRenderer (package/Runtime/GaussianSplatRenderer.cs) on top of
+the C ABI.  Same member names, argument meaning and order of operations as the C# component for
+the hot path; everything it does is a call into libgsplat_b200.so (there is no CPU path here).
+
+  C#                                          here
+  ------------------------------------------  ------------------------------------------------
+  OnEnable -> CreateResourcesForAsset (:373)   GaussianSplatRenderer(asset)  -> gs_asset_upload
+  SortPoints(cmd, cam, matrix)        (:612)   SortPoints(cam)               -> gs_sort
+  CalcViewData(cmb, cam)              (:579)   CalcViewData(cam)             -> gs_calc_view
+  cmb.DrawProcedural(matSplats)       (:165)   DrawSplats(cam, rt)           -> gs_render
+  composite DrawProcedural            (:206)   Composite(rt, target)         -> gs_composite
+  SortAndRenderSplats(cam, cmb)       (:108)   SortAndRenderSplats(cam, ...) -> gs_frame
+  OnDisable / DisposeResourcesForAsset(:533)   Dispose()
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+from .asset import GaussianSplatAsset
+from .camera import Camera, colmajor
+
+_PIX_DTYPES = {N.GS_PIX_RGBA16F: np.float16, N.GS_PIX_RGBA32F: np.float32}
+
+
+class GaussianSplatContext:
+    """One per CUDA device (GsContext)."""
+
+    def __init__(self, device: int = 0, stream: int = 0):
+        self._lib = N.native()
+        h = C.c_void_p()
+        N.check(None, self._lib.gs_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def sync(self):
+        N.check(self.handle, self._lib.gs_sync(self.handle))
+
+    def set_timing(self, enabled: bool):
+        N.check(self.handle, self._lib.gs_set_timing(self.handle, 1 if enabled else 0))
+
+    def stage_times(self) -> N.GsStageTimes:
+        t = N.GsStageTimes()
+        N.check(self.handle, self._lib.gs_get_stage_times(self.handle, C.byref(t)))
+        return t
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.gs_context_stream(self.handle) or 0)
+
+    def sort_pairs(self, keys: np.ndarray, payload: np.ndarray):
+        """GpuSorting.Dispatch on host arrays (in place)."""
+        assert keys.dtype == np.uint32 and payload.dtype == np.uint32 and keys.size == payload.size
+        assert keys.flags.c_contiguous and payload.flags.c_contiguous
+        N.check(self.handle, self._lib.gs_sort_pairs_host(self.handle, keys.ctypes.data, payload.ctypes.data, keys.size))
+
+    def sort_pairs_device(self, d_keys: int, d_payload: int, count: int):
+        N.check(self.handle, self._lib.gs_sort_pairs_device(self.handle, d_keys, d_payload, count))
+
+    def close(self):
+        if self.handle:
+            self._lib.gs_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _image(arr, width: int, height: int) -> N.GsImage:
+    """numpy (host) array or torch CUDA tensor of shape (H, W, 4), float16/float32 -> GsImage."""
+    im = N.GsImage()
+    im.width, im.height = width, height
+    if isinstance(arr, np.ndarray):
+        if arr.shape != (height, width, 4) or not arr.flags.c_contiguous:
+            raise ValueError("image must be C-contiguous (H, W, 4)")
+        if arr.dtype == np.float16:
+            im.format = N.GS_PIX_RGBA16F
+        elif arr.dtype == np.float32:
+            im.format = N.GS_PIX_RGBA32F
+        else:
+            raise ValueError("image dtype must be float16 or float32")
+        im.data, im.memory = arr.ctypes.data, N.GS_MEM_HOST
+        im.row_pitch_bytes = arr.strides[0]
+        return im
+    # torch tensor (duck-typed so torch stays optional)
+    if tuple(arr.shape) != (height, width, 4) or not arr.is_contiguous():
+        raise ValueError("image must be contiguous (H, W, 4)")
+    es = arr.element_size()
+    im.format = N.GS_PIX_RGBA16F if es == 2 else N.GS_PIX_RGBA32F
+    im.data = arr.data_ptr()
+    im.memory = N.GS_MEM_DEVICE if arr.is_cuda else N.GS_MEM_HOST
+    im.row_pitch_bytes = width * 4 * es
+    return im
+
+
+def make_frame_params(cam: Camera, localToWorld=None, splat_scale=1.0, opacity_scale=1.0, sh_order=3, sh_only=False, cutouts=None,
+                      deleted_bits=None, splat_count=0):
+    """The uniforms C# binds in CalcViewData / SortPoints (R/GaussianSplatRenderer.cs:586-606,617-631).
+    Returns (GsFrameParams, keepalive list for the borrowed host pointers)."""
+    fp = N.GsFrameParams()
+    o2w = np.eye(4, dtype=np.float32) if localToWorld is None else np.asarray(localToWorld, np.float32)
+    w2o = np.linalg.inv(o2w.astype(np.float64)).astype(np.float32)
+    for name, m in (("mat_object_to_world", o2w), ("mat_world_to_object", w2o), ("mat_view", cam.worldToCameraMatrix),
+                    ("mat_proj_gpu", cam.gpuProjectionMatrix(True))):
+        getattr(fp, name)[:] = colmajor(m).tolist()
+    fp.screen_w, fp.screen_h = float(cam.pixelWidth), float(cam.pixelHeight)
+    fp.cam_pos_world[:] = [float(v) for v in np.asarray(cam.position, np.float32)]
+    fp.splat_scale, fp.opacity_scale = float(splat_scale), float(opacity_scale)
+    fp.sh_order, fp.sh_only = int(sh_order), 1 if sh_only else 0
+    keep = []
+    if cutouts:
+        arr = (N.GsCutout * len(cutouts))()
+        for i, (m, tf) in enumerate(cutouts):
+            arr[i].mat[:] = colmajor(m).tolist()
+            arr[i].type_and_flags = int(tf)
+        fp.cutouts, fp.cutout_count = C.cast(arr, C.c_void_p), len(cutouts)
+        keep.append(arr)
+    if deleted_bits is not None:
+        bits = np.ascontiguousarray(deleted_bits, np.uint32)
+        assert bits.size >= (splat_count + 31) // 32
+        fp.deleted_bits = bits.ctypes.data
+        keep.append(bits)
+    return fp, keep
+
+
+class GaussianSplatRenderer:
+    def __init__(self, asset: GaussianSplatAsset, context: Optional[GaussianSplatContext] = None):
+        self.context = context or GaussianSplatContext(0)
+        self._lib = self.context._lib
+        self.m_Asset = asset
+        # serialized knobs, R/GaussianSplatRenderer.cs:225-251
+        self.m_SplatScale = 1.0
+        self.m_OpacityScale = 1.0
+        self.m_SHOrder = 3
+        self.m_SHOnly = False
+        self.m_SortNthFrame = 1
+        self.m_FrameCounter = 0
+        self.localToWorldMatrix = np.eye(4, dtype=np.float32)  # transform of the GameObject
+        self.m_Cutouts = []          # list of (4x4 matrix, type_and_flags)
+        self.m_DeletedBits = None    # np.uint32[ceil(N/32)] or None
+        self.blend_mode = N.GS_BLEND_FP16_ROP
+        self.partition = (0, 0, 1)   # index, count, band_rows
+        d = asset.desc()
+        h = C.c_void_p()
+        N.check(self.context.handle, self._lib.gs_asset_upload(self.context.handle, C.byref(d), C.byref(h)))
+        self._asset = h
+        self._keep = None
+
+    # -- resources ---------------------------------------------------------------------------
+    @property
+    def splatCount(self) -> int:
+        return self.m_Asset.splatCount
+
+    def Dispose(self):
+        if self._asset:
+            self._lib.gs_asset_destroy(self._asset)
+            self._asset = None
+
+    def __del__(self):
+        try:
+            self.Dispose()
+        except Exception:
+            pass
+
+    def ResetOrder(self):
+        N.check(self.context.handle, self._lib.gs_asset_reset_order(self._asset))
+
+    # -- uniforms ------------------------------------------------------------------------------
+    def frame_params(self, cam: Camera) -> N.GsFrameParams:
+        fp, self._keep = make_frame_params(cam, self.localToWorldMatrix, self.m_SplatScale, self.m_OpacityScale, self.m_SHOrder,
+                                           self.m_SHOnly, self.m_Cutouts, self.m_DeletedBits, self.splatCount)
+        return fp
+
+    def _options(self) -> N.GsRenderOptions:
+        o = N.GsRenderOptions()
+        o.blend_mode = self.blend_mode
+        o.partition_index, o.partition_count, o.band_rows = self.partition
+        return o
+
+    # -- the hot path ----------------------------------------------------------------------------
+    def SortPoints(self, cam: Camera):
+        fp = self.frame_params(cam)
+        N.check(self.context.handle, self._lib.gs_sort(self.context.handle, self._asset, C.byref(fp)))
+
+    def CalcViewData(self, cam: Camera):
+        fp = self.frame_params(cam)
+        N.check(self.context.handle, self._lib.gs_calc_view(self.context.handle, self._asset, C.byref(fp)))
+
+    def DrawSplats(self, cam: Camera, rt):
+        fp, opt = self.frame_params(cam), self._options()
+        im = _image(rt, cam.pixelWidth, cam.pixelHeight)
+        N.check(self.context.handle, self._lib.gs_render(self.context.handle, self._asset, C.byref(fp), C.byref(opt), C.byref(im)))
+
+    def Composite(self, rt, camera_target):
+        h, w = rt.shape[0], rt.shape[1]
+        a, b = _image(rt, w, h), _image(camera_target, w, h)
+        N.check(self.context.handle, self._lib.gs_composite(self.context.handle, C.byref(a), C.byref(b)))
+
+    def SortAndRenderSplats(self, cam: Camera, rt=None, camera_target=None):
+        """One frame: sort every m_SortNthFrame-th call (:120-121), view-calc, draw, optional composite."""
+        do_sort = 1 if (self.m_FrameCounter % max(1, int(self.m_SortNthFrame)) == 0) else 0
+        self.m_FrameCounter += 1
+        fp, opt = self.frame_params(cam), self._options()
+        a = _image(rt, cam.pixelWidth, cam.pixelHeight) if rt is not None else None
+        b = _image(camera_target, cam.pixelWidth, cam.pixelHeight) if camera_target is not None else None
+        N.check(self.context.handle,
+                self._lib.gs_frame(self.context.handle, self._asset, C.byref(fp), C.byref(opt), do_sort,
+                                   C.byref(a) if a is not None else None, C.byref(b) if b is not None else None))
+
+    # -- test hooks --------------------------------------------------------------------------------
+    def readback_order(self) -> np.ndarray:
+        out = np.empty(self.splatCount, np.uint32)
+        N.check(self.context.handle, self._lib.gs_readback_order(self._asset, out.ctypes.data))
+        return out
+
+    def readback_keys(self) -> np.ndarray:
+        out = np.empty(self.splatCount, np.uint32)
+        N.check(self.context.handle, self._lib.gs_readback_keys(self._asset, out.ctypes.data))
+        return out
+
+    def readback_view(self) -> np.ndarray:
+        out = np.empty((self.splatCount, 10), np.uint32)
+        N.check(self.context.handle, self._lib.gs_readback_view(self._asset, out.ctypes.data))
+        return out
+
+    def upload_order(self, order: np.ndarray):
+        order = np.ascontiguousarray(order, np.uint32)
+        assert order.size == self.splatCount
+        N.check(self.context.handle, self._lib.gs_upload_order(self._asset, order.ctypes.data))
