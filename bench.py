@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the hot path (BASELINE.json):
+Msplats/s (= splat_count / frame time) for bicycle-sized synthetic scene, 6,131,954 splats,
+Medium quality, 1200x797 (configs[1]), full frame = CSCalcDistances + radix sort + CSCalcViewData +
+draw/blend, every frame sorted (m_SortNthFrame = 1).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`value`   : device-resident throughput (asset in HBM, render target stays in HBM), CUDA events.
+`e2e`     : the same frame through the public call with HOST buffers: per step the uniforms go
+            host->device and the RGBA16F render target comes back into pinned host memory.
+`roofline`: the radix-sort digit pass (k_onesweep), the kernel BASELINE.json's metric names
+            ("radix-sort GB/s vs HBM peak"); per-stage numbers are under "stages".
+`cpu_baseline` / --impl reference: the CPU restatement of the reference's shaders (oracle/), all
+            host cores -- the reference has no CPU implementation of this path
+            and its C#/HLSL cannot run here, so kind = "port".
+N > 1     : screen-tile partition: every rank sorts + view-calcs the replicated asset,
+            composites only its own tile bands, then ONE all-gather of the band buffers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_SPLATS = 6_131_954          # bicycle, SURVEY.md 0 F5
+WIDTH, HEIGHT = 1200, 797     # readme.md:79-84
+FOV = 39.09651                # E/GaussianSplatValidator.cs:51
+SEED = 0x5EED0002
+SORT_BYTES_PER_PAIR_PASS = 16.0   # one digit pass: read key+payload, write key+payload
+FRAME_BYTES_PER_SPLAT = 212.5     # SURVEY.md 8d, Medium
+SORT_BYTES_PER_PAIR = 68.0
+
+
+def make_scene(n=N_SPLATS, quality="Medium"):
+    import unitygaussiansplatting_b200 as g
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, n, SEED, quality)
+    cam = g.Camera(position=np.array([0.0, 0.5, -6.0]), rotation=g.look_rotation([0, 0, 1]), fieldOfView=FOV, pixelWidth=WIDTH,
+                   pixelHeight=HEIGHT)
+    return g, asset, cam
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.path = "/tmp/gs_clocks_%d.csv" % os.getpid()
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_frame(O, asset, fp, threads):
+    """One full frame of the CPU restatement; returns seconds per stage."""
+    order = np.arange(asset.splatCount, dtype=np.uint32)
+    t0 = time.perf_counter()
+    keys = O.calc_distances(asset, fp, order, threads)
+    t1 = time.perf_counter()
+    O.sort_pairs(keys, order, threads)
+    t2 = time.perf_counter()
+    view = O.calc_view(asset, fp, threads)
+    t3 = time.perf_counter()
+    O.render(view, order, WIDTH, HEIGHT, 0, threads)
+    t4 = time.perf_counter()
+    return {"distances": t1 - t0, "sort": t2 - t1, "view": t3 - t2, "draw": t4 - t3, "total": t4 - t0}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference's shaders on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import gs_oracle_py as O
+    g, asset, cam = make_scene()
+    fp, _keep = g.make_frame_params(cam)
+    threads = O.max_threads()
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_frame(O, asset, fp, threads)
+    times = [cpu_frame(O, asset, fp, threads) for _ in range(max(1, min(args.steps, 3)))]
+    t = statistics.mean(x["total"] for x in times)
+    val = N_SPLATS / t / 1e6
+    line = {"impl": "reference", "metric": "splat throughput, full frame (sort + view-calc + draw)", "value": val, "unit": "Msplats/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "bicycle-sized synthetic: 6131954 splats, Medium, 1200x797, sort every frame"},
+            "cpu_baseline": {"value": val, "unit": "Msplats/s", "cores": threads, "kind": "port",
+                             "sample": "full frames of the whole workload (steps capped at 3); CPU restatement of the reference's "
+                                       "HLSL -- the reference has no CPU path"},
+            "e2e": {"value": val, "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "stages_ms": {k: statistics.mean(x[k] for x in times) * 1e3 for k in times[0]}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    g, asset, cam = make_scene()
+    from unitygaussiansplatting_b200 import _native as NV
+    from unitygaussiansplatting_b200 import multigpu as MG
+    stream = torch.cuda.Stream()
+    ctx = g.GaussianSplatContext(local, stream.cuda_stream)
+    r = g.GaussianSplatRenderer(asset, ctx)
+    part = MG.BandPartition(cam.pixelHeight, world, rank)
+    r.partition = part.options()
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        rt_dev = torch.zeros((HEIGHT, WIDTH, 4), dtype=torch.float16, device=dev)
+        gathered = MG.alloc_gather(part, WIDTH, dev) if world > 1 else None
+
+        def step_device():
+            if world == 1:
+                r.SortAndRenderSplats(cam, rt=rt_dev)
+            else:
+                MG.render_partitioned(r, cam, part, gathered, rt_dev, stream)
+
+        # ---- value: inputs and outputs resident in HBM ----
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        launches0 = ctx.stage_times().kernel_launches
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = ctx.stage_times().kernel_launches - launches0
+        t = torch.tensor([ms_total], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / args.steps
+
+        # ---- per-stage device times (CUDA events inside the library, same stream) ----
+        ctx.set_timing(True)
+        stage_acc = {}
+        reps = min(args.steps, 20)
+        for _ in range(reps):
+            step_device()
+            st = ctx.stage_times()
+            for k in ("distances_ms", "sort_ms", "view_ms", "bin_ms", "raster_ms"):
+                stage_acc.setdefault(k, []).append(getattr(st, k))
+            stage_acc.setdefault("sort_pass_ms", []).append(list(st.sort_pass_ms))
+            stage_acc.setdefault("tile_entries", []).append(int(st.tile_entries))
+        ctx.set_timing(False)
+        stages = {k: statistics.median(v) for k, v in stage_acc.items() if k not in ("sort_pass_ms", "tile_entries")}
+        pass_ms = [statistics.median(p[i] for p in stage_acc["sort_pass_ms"]) for i in range(4)]
+        tile_entries = int(statistics.median(stage_acc["tile_entries"]))
+
+        # ---- e2e: host buffers through the public call ----
+        pinned = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float16, pin_memory=True)
+        host_rt = pinned.numpy()
+        e2e_ms = None
+        if world == 1:
+            for _ in range(args.warmup):
+                r.SortAndRenderSplats(cam, rt=host_rt)
+            barrier()
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(args.steps):
+                r.SortAndRenderSplats(cam, rt=host_rt)   # uniforms H2D as kernel arguments, image D2H + sync inside
+            e1.record(stream)
+            barrier()
+            e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+        else:
+            for _ in range(args.warmup):
+                MG.render_partitioned(r, cam, part, gathered, rt_dev, stream)
+                pinned.copy_(rt_dev, non_blocking=True); stream.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                MG.render_partitioned(r, cam, part, gathered, rt_dev, stream)
+                if rank == 0:
+                    pinned.copy_(rt_dev, non_blocking=True)
+                stream.synchronize()
+            barrier()
+            tt = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tt.item()) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    sort_pass = statistics.mean(pass_ms) if any(pass_ms) else None
+    roofline = None
+    if sort_pass:
+        ach = N_SPLATS * SORT_BYTES_PER_PAIR_PASS / (sort_pass * 1e-3) / 1e9
+        roofline = {"kernel": "k_onesweep (one 8-bit digit pass of the radix sort, 4 launches per frame)", "bound": "hbm",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": N_SPLATS * SORT_BYTES_PER_PAIR_PASS, "launch_ms": sort_pass, "peak_source": peak_src}
+    stage_report = {k: v for k, v in stages.items()}
+    stage_report["sort_pass_ms"] = pass_ms
+    stage_report["tile_entries"] = tile_entries
+    if stages.get("sort_ms"):
+        stage_report["sort_gbs_68B"] = N_SPLATS * SORT_BYTES_PER_PAIR / (stages["sort_ms"] * 1e-3) / 1e9
+        stage_report["sort_frac_of_peak"] = stage_report["sort_gbs_68B"] / peak
+    if stages.get("view_ms"):
+        stage_report["view_gbs_88B"] = N_SPLATS * 88.25 / (stages["view_ms"] * 1e-3) / 1e9
+    if stages.get("distances_ms"):
+        stage_report["distances_gbs_12B"] = N_SPLATS * 12.25 / (stages["distances_ms"] * 1e-3) / 1e9
+    stage_report["frame_frac_of_hbm_roofline"] = (N_SPLATS * FRAME_BYTES_PER_SPLAT + WIDTH * HEIGHT * 8) / (ms_step * 1e-3) / 1e9 / peak
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import gs_oracle_py as O
+        fp, _keep = g.make_frame_params(cam)
+        threads = O.max_threads()
+        ct = cpu_frame(O, asset, fp, threads)
+        cpu = {"value": N_SPLATS / ct["total"] / 1e6, "unit": "Msplats/s", "cores": threads, "kind": "port",
+               "sample": "one full frame of the same workload (%.1f s): distances %.0f ms, sort %.0f ms, view %.0f ms, draw %.0f ms"
+                         % (ct["total"], ct["distances"] * 1e3, ct["sort"] * 1e3, ct["view"] * 1e3, ct["draw"] * 1e3)}
+
+    line = {
+        "metric": "splat throughput, full frame (sort + view-calc + draw)", "value": N_SPLATS / (ms_step * 1e-3) / 1e6,
+        "unit": "Msplats/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "bicycle-sized synthetic (BASELINE configs[1]): 6131954 splats, Medium, 1200x797, fov 39.1, sort every frame",
+                   "parallelism": "tile-band partition x%d + 1 all-gather" % world if world > 1 else "single GPU",
+                   "l2": "inputs (296 MB asset + 245 MB view + sort buffers) exceed the 126 MB L2; no explicit flush",
+                   "blend": "fp16 ROP emulation (reference-exact)"},
+        "fps": 1e3 / ms_step, "published_reference": {"fps": 147, "ms": 6.8, "hardware": "RTX 3080 Ti, readme.md:84"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": N_SPLATS / (e2e_ms * 1e-3) / 1e6, "unit": "Msplats/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 344, "d2h_bytes_per_step": WIDTH * HEIGHT * 8},
+        "roofline": roofline, "stages": stage_report, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,7 +119,9 @@ typedef enum GsBlendMode { GS_BLEND_FP16_ROP = 0, GS_BLEND_FP32 = 1 } GsBlendMod
 
 typedef struct GsRenderOptions {
   uint32_t blend_mode;        /* GsBlendMode */
-  uint32_t reserved;
+  uint32_t band_packed;       /* 1: rt holds only this partition's tile rows, packed: own tile row k -> pixel rows
+                                 [16k, 16k+16); rt->height must be 16 * (number of own tile rows).  This is the
+                                 send buffer of the all-gather. */
   /* Screen-tile partition for multi-GPU: this context composites only
    * tile rows r with (r / band_rows) % partition_count == partition_index.
    * partition_count 0 or 1 = whole image. */
@@ -182,6 +184,13 @@ GS_API int gs_composite(GsContext *ctx, const GsImage *rt, GsImage *camera_targe
  * (the RT then lives only in library scratch). */
 GS_API int gs_frame(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp,
                     const GsRenderOptions *opt, int do_sort, GsImage *rt, GsImage *camera_target);
+
+/* Multi-GPU epilogue: `gathered` is the all-gather of every partition's band-packed
+ * render target, [partition_count][rows_per_partition][width] pixels in DEVICE memory, where
+ * rows_per_partition = 16 * max over partitions of own tile rows.  Writes the assembled width x height
+ * image (device or host) in normal row order. */
+GS_API int gs_unshuffle_bands(GsContext *ctx, const void *gathered, uint32_t partition_count, uint32_t band_rows,
+                              uint32_t rows_per_partition, uint32_t pixel_format, GsImage *out);
 
 /* ---- stand-alone sorter (GpuSorting.Dispatch, R/GpuSorting.cs:142-198) ----------- */
 /* Stable ascending sort of `count` (uint32 key, uint32 payload) pairs in place in DEVICE

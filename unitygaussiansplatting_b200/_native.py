@@ -58,7 +58,7 @@ class GsImage(C.Structure):
 
 
 class GsRenderOptions(C.Structure):
-    _fields_ = [("blend_mode", C.c_uint32), ("reserved", C.c_uint32), ("partition_index", C.c_uint32),
+    _fields_ = [("blend_mode", C.c_uint32), ("band_packed", C.c_uint32), ("partition_index", C.c_uint32),
                 ("partition_count", C.c_uint32), ("band_rows", C.c_uint32), ("reserved1", C.c_uint32)]
 
 
@@ -93,6 +93,7 @@ NATIVE_SYMBOLS = {
     "gs_composite": (C.c_int, [C.c_void_p, C.POINTER(GsImage), C.POINTER(GsImage)]),
     "gs_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GsFrameParams), C.POINTER(GsRenderOptions), C.c_int,
                            C.POINTER(GsImage), C.POINTER(GsImage)]),
+    "gs_unshuffle_bands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(GsImage)]),
     "gs_sort_pairs_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "gs_sort_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "gs_readback_order": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -471,12 +471,13 @@ int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRend
   if (rc) return rc;
   if (!as->view_valid || as->view_w != (uint32_t)fp->screen_w || as->view_h != (uint32_t)fp->screen_h)
     return fail(ctx, GS_ERR_NOT_READY, "gs_render needs gs_calc_view for the same screen size first");
-  const uint32_t W = (uint32_t)fp->screen_w, H = (uint32_t)fp->screen_h;
+  const uint32_t W = (uint32_t)fp->screen_w;
   uint32_t pitch = 0;
-  if ((rc = image_ok(ctx, rt, W, H, &pitch))) return rc;
   GsRenderOptions opt = opt_in ? *opt_in : default_opts();
   if (opt.blend_mode > GS_BLEND_FP32) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad blend mode");
   FrameConsts fc = make_frame_consts(fp);
+  const uint32_t H = opt.band_packed ? partition_own_tile_rows(opt, fc.tilesY) * kTile : (uint32_t)fp->screen_h;
+  if ((rc = image_ok(ctx, rt, W, H, &pitch))) return rc;
   for (int e = EV_BIN1; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
   rec(ctx, EV_VIEW1);
   if (rt->memory == GS_MEM_DEVICE) return do_render(ctx, as, fc, opt, rt->data, pitch, rt->format);
@@ -528,13 +529,15 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
   int rc = check_params(ctx, as, fp);
   if (rc) return rc;
   if (!rt && !tgt) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "gs_frame needs rt and/or camera_target");
-  const uint32_t W = (uint32_t)fp->screen_w, H = (uint32_t)fp->screen_h;
+  const uint32_t W = (uint32_t)fp->screen_w;
   GsRenderOptions opt = opt_in ? *opt_in : default_opts();
   if (opt.blend_mode > GS_BLEND_FP32) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad blend mode");
   uint32_t rt_pitch = 0, rt_fmt = GS_PIX_RGBA16F;
+  FrameConsts fc = make_frame_consts(fp);
+  const uint32_t H = opt.band_packed ? partition_own_tile_rows(opt, fc.tilesY) * kTile : (uint32_t)fp->screen_h;
+  if (opt.band_packed && tgt) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "band_packed output cannot be composited before the gather");
   if (rt) { if ((rc = image_ok(ctx, rt, W, H, &rt_pitch))) return rc; rt_fmt = rt->format; }
   for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
-  FrameConsts fc = make_frame_consts(fp);
   if (do_sort_flag && (rc = do_sort(ctx, as, fc))) return rc;
   if ((rc = do_view(ctx, as, fp, fc))) return rc;
   void *d_rt;
@@ -557,6 +560,29 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
     synced = tgt->memory != GS_MEM_DEVICE;
   }
   if ((rt && !rt_dev) || synced) return check_bin_overflow(ctx);
+  return GS_OK;
+}
+
+int gs_unshuffle_bands(GsContext *ctx, const void *gathered, uint32_t parts, uint32_t band_rows, uint32_t rows_pp, uint32_t fmt,
+                       GsImage *out) {
+  if (!ctx || !gathered || !out || parts == 0) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "null argument");
+  uint32_t pitch = 0;
+  int rc = image_ok(ctx, out, out->width, out->height, &pitch);
+  if (rc) return rc;
+  if (out->format != fmt) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "gathered and output pixel formats differ");
+  const uint32_t W = out->width, H = out->height;
+  if (out->memory == GS_MEM_DEVICE) {
+    launch_unshuffle(gathered, parts, band_rows, rows_pp, fmt, out->data, pitch, W, H, ctx->stream);
+    ctx->launches += 1;
+    GS_CUDA_TRY(ctx, cudaGetLastError());
+    return GS_OK;
+  }
+  const uint32_t tight = W * pix_bytes(fmt);
+  if ((rc = grow(ctx, &ctx->rt_scratch, &ctx->rt_bytes, (size_t)tight * H))) return rc;
+  launch_unshuffle(gathered, parts, band_rows, rows_pp, fmt, ctx->rt_scratch, tight, W, H, ctx->stream);
+  ctx->launches += 1;
+  GS_CUDA_TRY(ctx, cudaMemcpy2DAsync(out->data, pitch, ctx->rt_scratch, tight, tight, H, cudaMemcpyDeviceToHost, ctx->stream));
+  GS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return GS_OK;
 }
 

@@ -84,6 +84,9 @@ void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t 
                     const BinScratch &bs, const SortScratch &sc, cudaStream_t s);
 void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const uint32_t *view, const BinScratch &bs, void *rt,
                    uint32_t rt_pitch_bytes, uint32_t rt_format, const void *unused, cudaStream_t s);
+uint32_t partition_own_tile_rows(const GsRenderOptions &opt, uint32_t tilesY);
+void launch_unshuffle(const void *gathered, uint32_t parts, uint32_t band, uint32_t rows_pp, uint32_t fmt, void *out, uint32_t pitch,
+                      uint32_t W, uint32_t H, cudaStream_t s);
 void launch_composite(const void *rt, uint32_t rt_pitch, uint32_t rt_format, void *target, uint32_t tgt_pitch, uint32_t tgt_format,
                       uint32_t W, uint32_t H, cudaStream_t s);
 

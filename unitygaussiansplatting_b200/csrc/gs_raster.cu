@@ -210,7 +210,7 @@ __device__ __forceinline__ float round_half(float v) { return __half2float(__flo
 template <bool FP16_ROP, int OUT_FMT>
 __global__ void __launch_bounds__(256)
 k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, const uint32_t *__restrict__ tile_vals,
-         const uint2 *__restrict__ ranges, uint8_t *__restrict__ rt, uint32_t pitch) {
+         const uint2 *__restrict__ ranges, uint8_t *__restrict__ rt, uint32_t pitch, uint32_t band_packed) {
   __shared__ float4 s_a[256];  // cx, cy, i1x, i1y
   __shared__ float4 s_b[256];  // i2x, i2y, opacity, hx
   __shared__ float4 s_c[256];  // r, g, b, hy
@@ -294,7 +294,8 @@ k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, cons
   }
 
   if (in_image) {
-    uint8_t *row = rt + (size_t)py * pitch;
+    const uint32_t out_row = band_packed ? blockIdx.y * kTile + (py - ty * kTile) : py;
+    uint8_t *row = rt + (size_t)out_row * pitch;
     if (OUT_FMT == GS_PIX_RGBA16F) {
       uint2 o;
       o.x = f32tof16(d0) | (f32tof16(d1) << 16);
@@ -316,12 +317,37 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const uint
   const bool rop = opt.blend_mode == GS_BLEND_FP16_ROP;
   uint8_t *out = reinterpret_cast<uint8_t *>(rt);
   if (rt_format == GS_PIX_RGBA16F) {
-    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes);
-    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes);
+    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes, opt.band_packed);
+    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes, opt.band_packed);
   } else {
-    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes);
-    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes);
+    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes, opt.band_packed);
+    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes, opt.band_packed);
   }
+}
+
+uint32_t partition_own_tile_rows(const GsRenderOptions &opt, uint32_t tilesY) { return make_partition(opt).own_rows_below(tilesY); }
+
+// ---- 2b. multi-GPU epilogue: gathered band-packed targets -> one image ---------------------------
+__global__ void __launch_bounds__(256) k_unshuffle(const uint8_t *__restrict__ gathered, Partition part, uint32_t rows_pp, uint32_t px_bytes,
+                                                   uint8_t *__restrict__ out, uint32_t pitch, uint32_t W, uint32_t H) {
+  const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const uint32_t ty = y / kTile;
+  Partition owner = part;
+  owner.index = part.count > 1 ? (ty / part.band) % part.count : 0;
+  const uint32_t k = owner.own_rows_below(ty);
+  const uint8_t *src = gathered + ((size_t)owner.index * rows_pp + (size_t)k * kTile + (y - ty * kTile)) * W * px_bytes;
+  if (px_bytes == 8) reinterpret_cast<uint2 *>(out + (size_t)y * pitch)[x] = reinterpret_cast<const uint2 *>(src)[x];
+  else reinterpret_cast<uint4 *>(out + (size_t)y * pitch)[x] = reinterpret_cast<const uint4 *>(src)[x];
+}
+
+void launch_unshuffle(const void *gathered, uint32_t parts, uint32_t band, uint32_t rows_pp, uint32_t fmt, void *out, uint32_t pitch,
+                      uint32_t W, uint32_t H, cudaStream_t s) {
+  Partition p;
+  p.count = parts; p.index = 0; p.band = band ? band : 1;
+  dim3 grid((W + 31) / 32, (H + 7) / 8);
+  k_unshuffle<<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t *>(gathered), p, rows_pp, fmt == GS_PIX_RGBA16F ? 8u : 16u,
+                                   reinterpret_cast<uint8_t *>(out), pitch, W, H);
 }
 
 // ---- 3. composite (S/GaussianComposite.shader:35-39, Blend SrcAlpha OneMinusSrcAlpha :11) ------

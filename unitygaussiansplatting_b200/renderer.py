@@ -146,6 +146,7 @@ class GaussianSplatRenderer:
         self.m_DeletedBits = None    # np.uint32[ceil(N/32)] or None
         self.blend_mode = N.GS_BLEND_FP16_ROP
         self.partition = (0, 0, 1)   # index, count, band_rows
+        self.band_packed = False
         d = asset.desc()
         h = C.c_void_p()
         N.check(self.context.handle, self._lib.gs_asset_upload(self.context.handle, C.byref(d), C.byref(h)))
@@ -181,6 +182,7 @@ class GaussianSplatRenderer:
         o = N.GsRenderOptions()
         o.blend_mode = self.blend_mode
         o.partition_index, o.partition_count, o.band_rows = self.partition
+        o.band_packed = 1 if self.band_packed else 0
         return o
 
     # -- the hot path ----------------------------------------------------------------------------
@@ -194,7 +196,7 @@ class GaussianSplatRenderer:
 
     def DrawSplats(self, cam: Camera, rt):
         fp, opt = self.frame_params(cam), self._options()
-        im = _image(rt, cam.pixelWidth, cam.pixelHeight)
+        im = _image(rt, cam.pixelWidth, rt.shape[0])
         N.check(self.context.handle, self._lib.gs_render(self.context.handle, self._asset, C.byref(fp), C.byref(opt), C.byref(im)))
 
     def Composite(self, rt, camera_target):
@@ -207,7 +209,7 @@ class GaussianSplatRenderer:
         do_sort = 1 if (self.m_FrameCounter % max(1, int(self.m_SortNthFrame)) == 0) else 0
         self.m_FrameCounter += 1
         fp, opt = self.frame_params(cam), self._options()
-        a = _image(rt, cam.pixelWidth, cam.pixelHeight) if rt is not None else None
+        a = _image(rt, cam.pixelWidth, rt.shape[0]) if rt is not None else None
         b = _image(camera_target, cam.pixelWidth, cam.pixelHeight) if camera_target is not None else None
         N.check(self.context.handle,
                 self._lib.gs_frame(self.context.handle, self._asset, C.byref(fp), C.byref(opt), do_sort,
