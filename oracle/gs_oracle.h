@@ -24,7 +24,7 @@
  *   - normalize(v) = v / sqrt(dot(v,v)); length = sqrt; rcp = 1/x; all IEEE.
  *   - f32tof16 rounds to nearest even; f16tof32 exact.
  *   - exp() in the splat pixel shader is gso_exp_neg(): 2^(x*log2e) by magic-number
- *     range reduction and a fixed degree-5 polynomial (max rel. error 2.2e-7, the same
+ *     range reduction and a fixed degree-5 polynomial (max rel. error 7e-7 on [-8,0], the same
  *     class as a GPU's ex2.approx), so the discard test alpha < 1/255 is reproducible.
  *
  * Citations: S/ = package/Shaders, R/ = package/Runtime of the reference.

@@ -1,0 +1,136 @@
+"""The host-side packer (csrc/asset_creator.cpp) against the reference's documented layout, and
+encode -> oracle-decode round trips for every supported format."""
+import numpy as np
+import pytest
+
+from util import one_splat
+
+
+def _raw(g, kind, n, seed):
+    return g.generate_input_splats(kind, n, seed)
+
+
+def test_sizes_match_the_reference_formulas(g):
+    # R/GaussianSplatAsset.cs:152-203; readme.md:80 quotes 282 MB for bicycle at Medium
+    from unitygaussiansplatting_b200 import _native as N
+    import ctypes as C
+    sz = N.GsaSizes()
+    n = 6_131_954
+    assert N.asset_lib().gsa_calc_sizes(n, 2, 2, 2, 3, C.byref(sz)) == 0
+    assert (sz.tex_width, sz.tex_height) == (2048, 3008)
+    assert sz.pos_bytes == (n * 4 + 7) // 8 * 8 and sz.other_bytes == n * 8 and sz.sh_bytes == n * 32
+    assert sz.color_bytes == 2048 * 3008 * 4 and sz.chunk_bytes == ((n + 255) // 256) * 64
+    total = sz.pos_bytes + sz.other_bytes + sz.sh_bytes + sz.color_bytes + sz.chunk_bytes
+    assert abs(total / 2**20 - 282.3) < 0.1
+    assert N.asset_lib().gsa_calc_sizes(n, 0, 0, 0, 0, C.byref(sz)) == 0 and sz.chunk_bytes == 0   # lossless: no chunks
+    assert N.asset_lib().gsa_calc_sizes(n, 2, 2, 3, 3, C.byref(sz)) != 0    # BC7: out of scope
+    assert N.asset_lib().gsa_calc_sizes(n, 2, 2, 2, 4, C.byref(sz)) != 0    # clustered SH: out of scope
+
+
+def test_generation_is_deterministic(g):
+    a, b = _raw(g, g.SCENE_CLUSTERED, 5000, 7), _raw(g, g.SCENE_CLUSTERED, 5000, 7)
+    assert np.array_equal(a, b) and not np.array_equal(a, _raw(g, g.SCENE_CLUSTERED, 5000, 8))
+    assert np.isfinite(a).all()
+
+
+def test_morton_reorder(g):
+    from unitygaussiansplatting_b200 import _native as N
+    raw = _raw(g, g.SCENE_UNIFORM, 20000, 3)
+    before = raw.copy()
+    asset = g.create_asset(raw, "VeryHigh")     # lossless: `raw` is now just the reordered input
+    assert sorted(map(bytes, raw)) == sorted(map(bytes, before))
+    bmin, bmax = before[:, :3].min(0), before[:, :3].max(0)
+    assert np.array_equal(asset.boundsMin, bmin) and np.array_equal(asset.boundsMax, bmax)
+    inv = np.float32(1.0) / (bmax - bmin)
+    ip = ((raw[:, :3] - bmin) * inv * np.float32((1 << 21) - 1)).astype(np.uint32)
+    codes = np.array([N.asset_lib().gsa_morton_encode3(int(x), int(y), int(z)) for x, y, z in ip], np.uint64)
+    assert np.all(codes[1:] >= codes[:-1])
+    assert N.asset_lib().gsa_morton_encode3(1, 0, 0) == 1 and N.asset_lib().gsa_morton_encode3(0, 1, 0) == 2 and \
+        N.asset_lib().gsa_morton_encode3(0, 0, 1) == 4 and N.asset_lib().gsa_morton_encode3(0x1FFFFF, 0x1FFFFF, 0x1FFFFF) == (1 << 63) - 1
+
+
+def _rotmat(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _unpack_rot(packed):
+    # inverse of PackSmallest3Rotation (R/GaussianUtils.cs:46-76), float64
+    idx = int(round(packed[3] * 3))
+    xyz = packed[:3] * np.sqrt(2.0) - 1 / np.sqrt(2.0)
+    w = np.sqrt(max(0.0, 1 - float(xyz @ xyz)))
+    q = [xyz[0], xyz[1], xyz[2], w]
+    return {0: [w, xyz[0], xyz[1], xyz[2]], 1: [xyz[0], w, xyz[1], xyz[2]], 2: [xyz[0], xyz[1], w, xyz[2]], 3: q}[idx]
+
+
+@pytest.mark.parametrize("quality", ["VeryHigh", "High", "Medium"])
+def test_encode_decode_round_trip(g, O, quality):
+    raw = _raw(g, g.SCENE_CLUSTERED, 3000, 11)
+    src = raw.copy()
+    # reproduce the Morton permutation so decoded splat i can be compared with its source record
+    ref = g.create_asset(src.copy(), "VeryHigh")
+    order_src = src.copy()
+    g.create_asset(order_src, "VeryHigh")          # order_src is now the Morton-ordered, unmodified input
+    asset = g.create_asset(raw, quality)
+    tol = {"VeryHigh": dict(pos=0, scale=0, col=0, sh=0, op=0),
+           "High": dict(pos=2e-5, scale=6e-3, col=2e-3, sh=2e-3, op=1.5e-3),
+           "Medium": dict(pos=1.2e-3, scale=0.02, col=6e-3, sh=0.04, op=6e-3)}[quality]
+    for i in range(0, 3000, 7):
+        s, d = order_src[i], O.load_splat(asset, i)
+        chunk = order_src[(i // 256) * 256:(i // 256) * 256 + 256]
+        prange = (chunk[:, :3].max(0) - chunk[:, :3].min(0)).max() + 1e-5
+        assert np.abs(d["pos"] - s[0:3]).max() <= tol["pos"] * prange + 1e-6 * (quality != "VeryHigh")
+        assert np.abs(d["scale"] / s[55:58] - 1).max() <= tol["scale"]
+        assert np.abs(d["col"] - s[6:9]).max() <= tol["col"]
+        # opacity is stored as SquareCentered01(opacity), whose inverse has infinite slope at 0.5: compare in the stored domain
+        sq = lambda x: (x - 0.5) * abs(x - 0.5) * 2 + 0.5
+        assert abs(sq(float(d["opacity"])) - sq(float(s[54]))) <= tol["op"]
+        shrange = float(chunk[:, 9:54].max() - chunk[:, 9:54].min()) + 1e-5
+        assert np.abs(d["sh"].reshape(45) - s[9:54]).max() <= tol["sh"] * shrange
+        R0, R1 = _rotmat(_unpack_rot(s[58:62].astype(np.float64))), _rotmat(d["rot"].astype(np.float64))
+        assert np.abs(R0 - R1).max() < 6e-3       # 10-bit smallest-three
+    if quality == "VeryHigh":
+        assert asset.chunkData is None
+        assert np.array_equal(asset.posData[:3000 * 12].view(np.float32).reshape(-1, 3), order_src[:, :3])
+    else:
+        assert asset.chunkData is not None and asset.chunkData.nbytes == ((3000 + 255) // 256) * 64
+    assert ref.splatCount == 3000
+
+
+def test_pack_smallest3_and_rotation_decode_agree(g, O):
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        q = rng.standard_normal(4)
+        q /= np.linalg.norm(q)
+        asset = one_splat(g, quat=q)
+        d = O.load_splat(asset, 0)
+        idx0 = 0 if np.allclose(d["pos"], 0, atol=1e-6) else None
+        assert idx0 == 0
+        assert np.abs(_rotmat(q) - _rotmat(d["rot"].astype(np.float64))).max() < 6e-3
+        assert abs(np.linalg.norm(d["rot"]) - 1) < 3e-3   # DecodeRotation does not renormalise
+
+
+def test_unity_f32tof16_rounds_half_up_on_bit_12(g):
+    from unitygaussiansplatting_b200 import _native as N
+    L = N.asset_lib()
+    rng = np.random.default_rng(4)
+    v = (rng.random(5000).astype(np.float32) * 8 - 4)
+    got = np.array([L.gsa_f32tof16(float(x)) for x in v], np.uint32)
+    want = v.astype(np.float16).view(np.uint16).astype(np.uint32)
+    assert (got != want).mean() < 0.01 and np.abs(got.astype(np.int64) - want.astype(np.int64)).max() <= 1
+    assert L.gsa_f32tof16(1.0) == 0x3C00 and L.gsa_f32tof16(-2.0) == 0xC000 and L.gsa_f32tof16(65536.0) == 0x7C00
+    assert L.gsa_f32tof16(1.00048828125) == 0x3C01     # exact tie rounds up (RNE would give 0x3C00)
+
+
+def test_chunk_bounds_enclose_and_decode_is_inside_them(g, O):
+    raw = _raw(g, g.SCENE_CLUSTERED, 1000, 5)
+    asset = g.create_asset(raw, "Medium")
+    ch = asset.chunkData.view(np.uint32).reshape(-1, 16)
+    pos_minmax = ch[:, 4:10].view(np.float32).reshape(-1, 3, 2)
+    for i in range(0, 1000, 13):
+        d = O.load_splat(asset, i)
+        lo, hi = pos_minmax[i // 256, :, 0], pos_minmax[i // 256, :, 1]
+        assert np.all(d["pos"] >= lo - 1e-6) and np.all(d["pos"] <= hi + 1e-6)
+        assert 0.0 <= float(d["opacity"]) <= 1.0 and np.all(d["scale"] > 0)
