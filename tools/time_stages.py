@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Per-stage device times of the cfg2 frame (library CUDA events), for quick A/B on the GPU box."""
+import statistics
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
+import bench
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else bench.N_SPLATS
+g, asset, cam = bench.make_scene(n)
+ctx = g.GaussianSplatContext(0)
+r = g.GaussianSplatRenderer(asset, ctx)
+import torch
+rt = torch.zeros((cam.pixelHeight, cam.pixelWidth, 4), dtype=torch.float16, device="cuda")
+for _ in range(5):
+    r.SortAndRenderSplats(cam, rt=rt)
+ctx.set_timing(True)
+acc = {}
+for _ in range(30):
+    r.SortAndRenderSplats(cam, rt=rt)
+    st = ctx.stage_times()
+    for k in ("distances_ms", "sort_ms", "view_ms", "bin_ms", "raster_ms", "total_ms"):
+        acc.setdefault(k, []).append(getattr(st, k))
+    acc.setdefault("p", []).append(list(st.sort_pass_ms))
+print({k: round(statistics.median(v) * 1e3, 1) for k, v in acc.items() if k != "p"}, "us; passes",
+      [round(statistics.median(p[i] for p in acc["p"]) * 1e3, 1) for i in range(4)], "entries", int(st.tile_entries))

@@ -55,7 +55,7 @@ struct GsAsset {
   GsContext *ctx = nullptr;
   gs::AssetView av{};
   void *d_pos = nullptr, *d_other = nullptr, *d_sh = nullptr, *d_color = nullptr, *d_chunks = nullptr;
-  uint32_t *order = nullptr, *keys = nullptr, *view = nullptr, *rect = nullptr, *d_n = nullptr;
+  uint32_t *order = nullptr, *keys = nullptr, *key_table = nullptr, *view = nullptr, *rect = nullptr, *d_n = nullptr;
   bool view_valid = false;
   uint32_t view_w = 0, view_h = 0;
 };
@@ -171,13 +171,7 @@ static int ensure_bin_scratch(GsContext *ctx, uint32_t n, uint32_t tiles, uint32
     GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.block_sums, (size_t)blocks * 4));
     ctx->bin_blocks_cap = blocks;
   }
-  if (tiles > ctx->tiles_cap) {
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->bin.tile_start);
-    ctx->bin.tile_start = nullptr;
-    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.tile_start, (size_t)tiles * 8));
-    ctx->tiles_cap = tiles;
-  }
+  (void)tiles;
   return GS_OK;
 }
 
@@ -232,10 +226,11 @@ static int do_sort(GsContext *ctx, GsAsset *as, const FrameConsts &fc) {
   if (rc) return rc;
   rec(ctx, EV_BEGIN);
   GS_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sort.ghist, 0, 4 * 256 * 4, ctx->stream));
-  launch_calc_distances(as->av, fc, as->order, as->keys, ctx->sort.ghist, ctx->stream);
+  launch_calc_distances(as->av, fc, as->key_table, ctx->sort.ghist, ctx->stream);
   rec(ctx, EV_DIST);
   cudaEvent_t pe[5] = {ctx->ev[EV_SORT0], ctx->ev[EV_SORT1], ctx->ev[EV_SORT2], ctx->ev[EV_SORT3], ctx->ev[EV_SORT4]};
-  launch_sort_pairs(as->keys, as->order, as->d_n, as->av.n, 4, true, ctx->sort, ctx->stream, ctx->timing ? pe : nullptr);
+  launch_sort_pairs(as->keys, as->order, as->d_n, as->av.n, 4, 8, true, ctx->sort, ctx->stream, ctx->timing ? pe : nullptr,
+                    as->key_table);
   if (ctx->timing) for (int e = EV_SORT0; e <= EV_SORT4; ++e) ctx->ev_valid[e] = true;
   ctx->launches += 1 + 4;
   GS_CUDA_TRY(ctx, cudaGetLastError());
@@ -266,7 +261,7 @@ static int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const G
   rec(ctx, EV_BIN1);
   launch_raster(fc, opt, as->view, ctx->bin, d_rt, pitch, fmt, nullptr, ctx->stream);
   rec(ctx, EV_RASTER1);
-  ctx->launches += 3 + 3 + 1 + 1;
+  ctx->launches += 1 + 3 + 1;  // bin_emit, sort (hist + 2 passes), raster
   GS_CUDA_TRY(ctx, cudaGetLastError());
   return GS_OK;
 }
@@ -339,7 +334,7 @@ void gs_destroy(GsContext *ctx) {
   cudaFree(ctx->sort.alt_keys); cudaFree(ctx->sort.alt_vals); cudaFree(ctx->sort.lookback);
   cudaFree(ctx->sort.ghist); cudaFree(ctx->sort.tickets); cudaFree(ctx->d_scalar);
   cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
-  cudaFree(ctx->bin.tile_start); cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted);
+  cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted);
   for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -413,6 +408,7 @@ int gs_asset_upload(GsContext *ctx, const GsAssetDesc *d, GsAsset **out) {
       (e = up(&as->d_sh, d->sh, d->sh_bytes)) != cudaSuccess || (e = up(&as->d_color, d->color, d->color_bytes)) != cudaSuccess ||
       (chunk_count && (e = up(&as->d_chunks, d->chunks, (uint64_t)chunk_count * 64)) != cudaSuccess) ||
       (e = cudaMalloc(&as->order, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->keys, n * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&as->key_table, n * 4)) != cudaSuccess ||
       (e = cudaMalloc(&as->view, n * kViewStride + 16)) != cudaSuccess || (e = cudaMalloc(&as->rect, n * 4)) != cudaSuccess ||
       (e = cudaMalloc(&as->d_n, 4)) != cudaSuccess) {
     gs_asset_destroy(as);
@@ -436,7 +432,7 @@ void gs_asset_destroy(GsAsset *as) {
   if (!as) return;
   if (as->ctx) { cudaSetDevice(as->ctx->device); cudaStreamSynchronize(as->ctx->stream); }
   cudaFree(as->d_pos); cudaFree(as->d_other); cudaFree(as->d_sh); cudaFree(as->d_color); cudaFree(as->d_chunks);
-  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n);
+  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n);
   delete as;
 }
 
@@ -597,7 +593,7 @@ int gs_sort_pairs_device(GsContext *ctx, uint32_t *d_keys, uint32_t *d_payload, 
   for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
   cudaEvent_t pe[5] = {ctx->ev[EV_SORT0], ctx->ev[EV_SORT1], ctx->ev[EV_SORT2], ctx->ev[EV_SORT3], ctx->ev[EV_SORT4]};
   rec(ctx, EV_BEGIN);
-  launch_sort_pairs(d_keys, d_payload, ctx->d_scalar, count, 4, false, ctx->sort, ctx->stream, ctx->timing ? pe : nullptr);
+  launch_sort_pairs(d_keys, d_payload, ctx->d_scalar, count, 4, 8, false, ctx->sort, ctx->stream, ctx->timing ? pe : nullptr);
   if (ctx->timing) for (int e = EV_SORT0; e <= EV_SORT4; ++e) ctx->ev_valid[e] = true;
   ctx->launches += 5;
   GS_CUDA_TRY(ctx, cudaGetLastError());

@@ -50,8 +50,7 @@ __device__ __forceinline__ uint32_t footprint_tile_rect(const SplatFootprint &fp
 
 // ---- launchers (each enqueues on `s`, returns nothing; errors surface via cudaGetLastError) ----
 void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s);
-void launch_calc_distances(const AssetView &a, const FrameConsts &fc, const uint32_t *order, uint32_t *keys, uint32_t *ghist,
-                           cudaStream_t s);
+void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s);
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
                       uint32_t *rect, cudaStream_t s);
 
@@ -65,19 +64,20 @@ struct SortScratch {
 };
 constexpr uint32_t kSortTileItems = 4096;  // 256 threads x 16 keys
 size_t sort_lookback_words(uint32_t capacity, int passes);
-// Stable ascending LSD sort of (key,val) pairs on bits [0, 8*passes).  count is read from
+// Stable ascending LSD sort of (key,val) pairs on bits [0, bits*passes), bits in {6,7,8}.  count is read from
 // d_count (device) so the binner can sort a device-sized list; capacity bounds the grid.
 // ghist must already hold the per-pass digit counts when hist_ready, otherwise it is computed.
-// After an even number of passes the result is back in keys/vals.
-void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, uint32_t capacity, int passes, bool hist_ready,
-                       const SortScratch &sc, cudaStream_t s, cudaEvent_t *pass_events = nullptr);
+// After an even number of passes the result is back in keys/vals.  key_table != nullptr: the input keys are
+// key_table[vals[i]] (gathered inside pass 0; `keys` is then output only).
+void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, uint32_t capacity, int passes, int bits, bool hist_ready,
+                       const SortScratch &sc, cudaStream_t s, cudaEvent_t *pass_events = nullptr,
+                       const uint32_t *key_table = nullptr);
 
 // Binning + raster + composite (gs_raster.cu)
 struct BinScratch {
-  uint32_t *block_sums;    // scan partials
-  uint32_t *entry_count;   // [0] = total (tile,splat) entries, [1] = overflow flag
+  uint32_t *block_sums;    // [0] block ticket, [1..] look-back status of the fused count+scan+emit kernel
+  uint32_t *entry_count;   // [0] = (tile,splat) entries clamped to capacity, [1] = overflow flag, [2] = unclamped total
   uint32_t *tile_keys, *tile_vals;  // capacity entries each
-  uint32_t *tile_start;    // tiles+1
   uint32_t capacity;
 };
 void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,

@@ -54,71 +54,12 @@ __device__ __forceinline__ uint32_t rect_entries(uint32_t r, const Partition &p)
 constexpr int kBinItems = 4;
 constexpr int kBinBlock = 256 * kBinItems;
 
-// ---- 1a. per-block entry totals ---------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bin_count(const uint32_t *__restrict__ order, const uint32_t *__restrict__ rect, uint32_t n,
-                                                   Partition part, uint32_t *__restrict__ block_sums) {
-  __shared__ uint32_t s_w[8];
-  uint32_t sum = 0;
-  const uint32_t base = blockIdx.x * kBinBlock + threadIdx.x * kBinItems;
-#pragma unroll
-  for (int i = 0; i < kBinItems; ++i) {
-    uint32_t r = base + i;
-    if (r < n) sum += rect_entries(__ldg(rect + __ldg(order + r)), part);
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < 8; ++w) t += s_w[w];
-    block_sums[blockIdx.x] = t;
-  }
-}
+// ---- 1. count + scan + emit in ONE pass ---------------------------------------------------------
+// Blocks take their index by atomic ticket, publish their entry total with a LOCAL flag, resolve
+// their exclusive offset by a warp-parallel decoupled look-back (32 predecessors per probe), then
+// emit (tile id, splat id) entries in depth order.
+enum : uint32_t { kBinFlagLocal = 1u << 30, kBinFlagIncl = 2u << 30, kBinValMask = (1u << 30) - 1u };
 
-// ---- 1b. exclusive scan of the block totals (single CTA) ---------------------------------------
-__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t *__restrict__ block_sums, uint32_t nblocks, uint32_t capacity,
-                                                   uint32_t *__restrict__ entry_count) {
-  __shared__ uint32_t s_w[32];
-  __shared__ uint32_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < nblocks; base += 1024) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = (i < nblocks) ? block_sums[i] : 0u;
-    uint32_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= (uint32_t)o) inc += t;
-    }
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = s_w[lane], wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= (uint32_t)o) wi += t;
-      }
-      s_w[lane] = wi - w;
-    }
-    __syncthreads();
-    uint32_t excl = s_carry + s_w[warp] + inc - v;
-    if (i < nblocks) block_sums[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = excl + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    uint32_t total = s_carry;
-    entry_count[1] = total > capacity ? 1u : 0u;  // overflow: lists are truncated, the API reports it
-    entry_count[0] = total > capacity ? capacity : total;
-  }
-}
-
-// ---- 1c. emit (tile id, splat id) entries in depth order ----------------------------------------
 __device__ __forceinline__ void emit_entry(uint32_t e, uint32_t r, uint32_t id, uint32_t off, const Partition &p, uint32_t tilesX,
                                            uint32_t capacity, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
   const uint32_t x0 = r & 255u, y0 = (r >> 8) & 255u, x1 = (r >> 16) & 255u;
@@ -133,18 +74,26 @@ __device__ __forceinline__ void emit_entry(uint32_t e, uint32_t r, uint32_t id, 
 }
 
 __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ order, const uint32_t *__restrict__ rect, uint32_t n,
-                                                  Partition part, uint32_t tilesX, const uint32_t *__restrict__ block_sums,
-                                                  uint32_t capacity, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                                                  Partition part, uint32_t tilesX, volatile uint32_t *status, uint32_t *ticket,
+                                                  uint32_t nblocks, uint32_t capacity, uint32_t *__restrict__ keys,
+                                                  uint32_t *__restrict__ vals, uint32_t *__restrict__ entry_count) {
   __shared__ uint32_t s_w[8];
+  __shared__ uint32_t s_block, s_excl;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t base = blockIdx.x * kBinBlock + threadIdx.x * kBinItems;
+  if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t b = s_block;
+  const uint32_t base = b * kBinBlock + threadIdx.x * kBinItems;
   uint32_t id[kBinItems], rc[kBinItems], cnt[kBinItems], sum = 0;
 #pragma unroll
   for (int i = 0; i < kBinItems; ++i) {
     uint32_t r = base + i;
     id[i] = 0; rc[i] = kRectEmpty; cnt[i] = 0;
-    if (r < n) {
-      id[i] = __ldg(order + r);
+    if (r < n) id[i] = __ldg(order + r);
+  }
+#pragma unroll
+  for (int i = 0; i < kBinItems; ++i) {
+    if (base + i < n) {
       rc[i] = __ldg(rect + id[i]);
       cnt[i] = rect_entries(rc[i], part);
     }
@@ -158,9 +107,47 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
   }
   if (lane == 31) s_w[warp] = inc;
   __syncthreads();
-  uint32_t woff = 0;
-  for (uint32_t w = 0; w < warp; ++w) woff += s_w[w];
-  uint32_t off = block_sums[blockIdx.x] + woff + inc - sum;
+  uint32_t woff = 0, total = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < 8; ++w) {
+    const uint32_t c = s_w[w];
+    if (w < warp) woff += c;
+    total += c;
+  }
+  if (warp == 0) {
+    if (lane == 0) status[b] = (b == 0 ? kBinFlagIncl : kBinFlagLocal) | total;
+    uint32_t excl = 0;
+    if (b > 0) {
+      int top = (int)b - 1;
+      while (true) {
+        const int idx = top - (int)lane;
+        uint32_t v;
+        do {
+          v = idx >= 0 ? status[idx] : kBinFlagIncl;
+        } while (__any_sync(0xffffffffu, v == 0));
+        const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v & kBinFlagIncl) != 0);
+        const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;   // nearest predecessor that is already inclusive
+        uint32_t contrib = ((int)lane <= first) ? (v & kBinValMask) : 0u;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (incl_mask) break;
+        top -= 32;
+      }
+      if (lane == 0) status[b] = kBinFlagIncl | ((excl + total) & kBinValMask);
+    }
+    if (lane == 0) {
+      s_excl = excl;
+      if (b == nblocks - 1) {
+        const uint32_t all = excl + total;
+        entry_count[1] = all > capacity ? 1u : 0u;   // overflow: lists are truncated, the API reports it
+        entry_count[0] = all > capacity ? capacity : all;
+        entry_count[2] = all;
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t off = s_excl + woff + inc - sum;
 #pragma unroll
   for (int i = 0; i < kBinItems; ++i) {
     // small footprints: the owning lane writes them; large ones are spread over the warp
@@ -179,45 +166,62 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
   }
 }
 
-// ---- 1d. per-tile [start,end) after the stable sort by tile id -----------------------------------
-__global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ entry_count,
-                                                     uint2 *__restrict__ ranges) {
-  const uint32_t m = entry_count[0];
-  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < m; i += gridDim.x * 256) {
-    const uint32_t k = keys[i];
-    if (i == 0 || keys[i - 1] != k) ranges[k].x = i;
-    if (i + 1 == m || keys[i + 1] != k) ranges[k].y = i + 1;
-  }
-}
+int bin_sort_bits(uint32_t tiles) { return tiles <= 4096u ? 6 : tiles <= 16384u ? 7 : 8; }
 
 void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
                     const BinScratch &bs, const SortScratch &sc, cudaStream_t s) {
   const Partition part = make_partition(opt);
   const uint32_t tiles = fc.tilesX * fc.tilesY;
-  cudaMemsetAsync(bs.tile_start, 0, (size_t)tiles * sizeof(uint2), s);
-  if (!n) { cudaMemsetAsync(bs.entry_count, 0, 8, s); return; }
+  if (!n) { cudaMemsetAsync(bs.entry_count, 0, 16, s); return; }
   const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
-  k_bin_count<<<nblocks, 256, 0, s>>>(order, rect, n, part, bs.block_sums);
-  k_bin_scan<<<1, 1024, 0, s>>>(bs.block_sums, nblocks, bs.capacity, bs.entry_count);
-  k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, n, part, fc.tilesX, bs.block_sums, bs.capacity, bs.tile_keys, bs.tile_vals);
-  launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, 2, false, sc, s);
-  k_tile_ranges<<<148 * 8, 256, 0, s>>>(bs.tile_keys, bs.entry_count, reinterpret_cast<uint2 *>(bs.tile_start));
+  cudaMemsetAsync(bs.block_sums, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
+  k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, n, part, fc.tilesX, bs.block_sums + 1, bs.block_sums, nblocks, bs.capacity,
+                                     bs.tile_keys, bs.tile_vals, bs.entry_count);
+  launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, 2, bin_sort_bits(tiles), false, sc, s);
 }
 
 // ---- 2. raster ---------------------------------------------------------------------------------
 __device__ __forceinline__ float round_half(float v) { return __half2float(__float2half_rn(v)); }
 
+// first index in sorted keys[0,m) whose key is >= target; all 32 lanes of a warp cooperate
+__device__ __forceinline__ uint32_t lower_bound32(const uint32_t *__restrict__ keys, uint32_t m, uint32_t target, uint32_t lane) {
+  uint32_t lo = 0, hi = m;
+  while (hi - lo > 32) {
+    const uint32_t len = hi - lo;
+    const uint32_t p = lo + (uint32_t)(((uint64_t)len * (lane + 1)) / 33);   // lo < p < hi, increasing with lane
+    const uint32_t below = __ballot_sync(0xffffffffu, __ldg(keys + p) < target);
+    const int c = __popc(below);                                             // predicate is monotone over lanes
+    const uint32_t p_lo = __shfl_sync(0xffffffffu, p, c > 0 ? c - 1 : 0), p_hi = __shfl_sync(0xffffffffu, p, c < 32 ? c : 31);
+    if (c > 0) lo = p_lo + 1;
+    if (c < 32) hi = p_hi;
+  }
+  const uint32_t p = lo + lane;
+  const uint32_t below = __ballot_sync(0xffffffffu, p < hi && __ldg(keys + p) < target);
+  return lo + __popc(below);
+}
+
 template <bool FP16_ROP, int OUT_FMT>
 __global__ void __launch_bounds__(256)
-k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, const uint32_t *__restrict__ tile_vals,
-         const uint2 *__restrict__ ranges, uint8_t *__restrict__ rt, uint32_t pitch, uint32_t band_packed) {
+k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, const uint32_t *__restrict__ tile_keys,
+         const uint32_t *__restrict__ tile_vals, const uint32_t *__restrict__ entry_count, uint8_t *__restrict__ rt, uint32_t pitch,
+         uint32_t band_packed) {
   __shared__ float4 s_a[256];  // cx, cy, i1x, i1y
   __shared__ float4 s_b[256];  // i2x, i2y, opacity, hx
   __shared__ float4 s_c[256];  // r, g, b, hy
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tx = blockIdx.x, ty = part.kth_own_row(blockIdx.y);
-  const uint2 range = ranges[ty * fc.tilesX + tx];
+  // the tile's [start,end) in the tile-sorted entry list: two warp-wide 32-ary searches (5 probes for 10M entries)
+  __shared__ uint2 s_range;
+  if (warp == 0) {
+    const uint32_t m = __ldg(entry_count);
+    const uint32_t tile = ty * fc.tilesX + tx;
+    const uint32_t a = lower_bound32(tile_keys, m, tile, lane);
+    const uint32_t b = lower_bound32(tile_keys, m, tile + 1, lane);
+    if (lane == 0) s_range = make_uint2(a, b);
+  }
+  __syncthreads();
+  const uint2 range = s_range;
   const uint32_t bx = tx * kTile + (warp & 1) * 8, by = ty * kTile + (warp >> 1) * 4;
   const uint32_t px = bx + (lane & 7), py = by + (lane >> 3);
   const float pxc = (float)px + 0.5f, pyc = (float)py + 0.5f;
@@ -313,15 +317,14 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const uint
   const uint32_t rows = part.own_rows_below(fc.tilesY);
   if (!rows || !fc.tilesX) return;
   dim3 grid(fc.tilesX, rows);
-  const uint2 *ranges = reinterpret_cast<const uint2 *>(bs.tile_start);
   const bool rop = opt.blend_mode == GS_BLEND_FP16_ROP;
   uint8_t *out = reinterpret_cast<uint8_t *>(rt);
   if (rt_format == GS_PIX_RGBA16F) {
-    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes, opt.band_packed);
-    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes, opt.band_packed);
+    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
+    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
   } else {
-    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes, opt.band_packed);
-    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_vals, ranges, out, rt_pitch_bytes, opt.band_packed);
+    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
+    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
   }
 }
 

@@ -9,23 +9,27 @@
 //   * digit histograms for all passes come from one read of the keys (or for free from
 //     k_calc_distances, which wrote the keys in the first place);
 //   * each CTA takes a 4096-pair tile by atomic ticket (so a tile's predecessors are
-//     always resident: look-back cannot deadlock), ranks its keys with warp ballots
-//     (8 ballots per key build the match mask of equal digits, popc of the lower lanes is
-//     the stable rank, one lane bumps the warp-private shared histogram), publishes the
-//     tile's per-digit count with a LOCAL flag, walks back over predecessors' status words
-//     until it meets an INCLUSIVE one, then publishes its own inclusive prefix;
+//     always resident: look-back cannot deadlock), ranks its keys with warp-level digit
+//     matching (the match mask of equal digits gives the stable rank as a popc of the lower
+//     lanes; one lane bumps the warp-private shared histogram), publishes the tile's
+//     per-digit count with a LOCAL flag, walks back over predecessors' status words until
+//     it meets an INCLUSIVE one, then publishes its own inclusive prefix;
 //   * keys and payloads are first scattered inside shared memory into digit order, then
-//     written out in runs, so global stores are coalesced per digit run.
+//     written out in runs, so global stores are coalesced per digit run;
+//   * payloads are fetched only after ranking (their latency hides behind the look-back),
+//     which keeps the kernel at <= 64 registers and 4 CTAs/SM.
+// The digit width is a template parameter: depth keys use 4 x 8 bits, the tile binner sorts
+// 12..16-bit tile ids in 2 passes of 6..8 bits.
 // No tensor-core path: there is no contraction here, only byte/integer traffic.
+#include <cstdio>
+#include <cstdlib>
+
 #include "gs_kernels.cuh"
 
 namespace gs {
 
-constexpr int kSortThreads = 256;
-constexpr int kSortKPT = 16;
-static_assert(kSortThreads * kSortKPT == (int)kSortTileItems, "tile size");
-constexpr int kSortWarps = kSortThreads / 32;
-constexpr uint32_t kFlagLocal = 1u << 30, kFlagIncl = 2u << 30, kValMask = (1u << 30) - 1u;
+constexpr int kSortKPT = 16;   // keys per thread; a tile is THREADS * 16 pairs (4096 or 8192)
+enum : uint32_t { kFlagLocal = 1u << 30, kFlagIncl = 2u << 30, kValMask = (1u << 30) - 1u };
 
 size_t sort_lookback_words(uint32_t capacity, int passes) {
   size_t tiles = ((size_t)capacity + kSortTileItems - 1) / kSortTileItems;
@@ -33,9 +37,10 @@ size_t sort_lookback_words(uint32_t capacity, int passes) {
 }
 
 // ---- digit histograms of all passes in one read -------------------------------------------
-template <int PASSES>
+template <int PASSES, int BITS>
 __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ d_count,
                                                    uint32_t *__restrict__ ghist) {
+  constexpr uint32_t NB = 1u << BITS;
   __shared__ uint32_t sh[PASSES * 256];
   for (int i = threadIdx.x; i < PASSES * 256; i += 256) sh[i] = 0;
   __syncthreads();
@@ -48,13 +53,13 @@ __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t *__restrict__ 
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int p = 0; p < PASSES; ++p) atomicAdd(&sh[p * 256 + ((kk[q] >> (8 * p)) & 255u)], 1u);
+      for (int p = 0; p < PASSES; ++p) atomicAdd(&sh[p * 256 + ((kk[q] >> (BITS * p)) & (NB - 1))], 1u);
   }
   if (blockIdx.x == 0) {
     for (uint32_t i = (nvec << 2) + threadIdx.x; i < n; i += 256) {
       uint32_t k = keys[i];
 #pragma unroll
-      for (int p = 0; p < PASSES; ++p) atomicAdd(&sh[p * 256 + ((k >> (8 * p)) & 255u)], 1u);
+      for (int p = 0; p < PASSES; ++p) atomicAdd(&sh[p * 256 + ((k >> (BITS * p)) & (NB - 1))], 1u);
     }
   }
   __syncthreads();
@@ -65,7 +70,8 @@ __global__ void __launch_bounds__(256) k_sort_hist(const uint32_t *__restrict__ 
 }
 
 // ---- block-wide exclusive scan of one value per thread (256 threads) ------------------------
-__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *s_warp /*8*/) {
+template <int WARPS>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp /*WARPS*/) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = v;
 #pragma unroll
@@ -75,10 +81,10 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *s_
   }
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  uint32_t wsum = (lane < kSortWarps) ? s_warp[lane] : 0u;
+  uint32_t wsum = (lane < WARPS) ? s_warp[lane] : 0u;
   uint32_t winc = wsum;
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
+  for (int o = 1; o < WARPS; o <<= 1) {
     uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
     if (lane >= (uint32_t)o) winc += t;
   }
@@ -87,58 +93,148 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *s_
   return wexcl + inc - v;
 }
 
+// Equal-digit mask by BITS ballots.  (__match_any_sync was measured 2.4x slower than 8 ballots on B200:
+// tools/mb/mb_match.cu, 1953 vs 812 ns per warp-op at 64 resident warps/SM.)
+template <int BITS>
+__device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+  uint32_t m = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < BITS; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? bal : ~bal;
+  }
+  return m;
+}
+
 // ---- one digit pass -------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSortThreads)
+__device__ __forceinline__ uint64_t gtime() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define GS_TRACE(slot) do { if (trace && tid == 0) trace[(size_t)tile * 8 + (slot)] = gtime(); } while (0)
+
+// GATHER: the keys of this pass are keys_src[payload] (pass 0 of the depth sort reads the per-splat key
+// table through last frame's order, S/SplatUtilities.compute:76-81, without a separate gather pass).
+template <int BITS, bool GATHER, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_onesweep(const uint32_t *__restrict__ src_k, const uint32_t *__restrict__ src_v, uint32_t *__restrict__ dst_k,
            uint32_t *__restrict__ dst_v, const uint32_t *__restrict__ d_count, int shift, const uint32_t *__restrict__ ghist,
-           volatile uint32_t *lookback, uint32_t *ticket) {
-  __shared__ uint32_t s_keys[kSortTileItems];
-  __shared__ uint32_t s_vals[kSortTileItems];
-  __shared__ uint32_t s_whist[kSortWarps][256];
-  __shared__ uint32_t s_dig_start[256];
-  __shared__ uint32_t s_off[256];
+           volatile uint32_t *lookback, uint32_t *ticket, uint64_t *trace) {
+  constexpr uint32_t NB = 1u << BITS;
+  constexpr uint32_t kTileItems = THREADS * kSortKPT;
+  constexpr int kSortWarps = THREADS / 32;
+  constexpr int kSortThreads = THREADS;
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  uint2 *s_kv = reinterpret_cast<uint2 *>(s_dyn);                                         // [kTileItems]
+  uint32_t (*s_whist)[NB] = reinterpret_cast<uint32_t (*)[NB]>(s_dyn + kTileItems * 8);    // [kSortWarps][NB]
+  __shared__ uint32_t s_hist[NB];
+  __shared__ uint32_t s_dig_start[NB];
+  __shared__ uint32_t s_off[NB];
   __shared__ uint32_t s_scan[kSortWarps];
   __shared__ uint32_t s_tile;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (uint32_t d = tid; d < NB; d += kSortThreads) s_hist[d] = 0;
+#pragma unroll
+  for (uint32_t d = lane; d < NB; d += 32) s_whist[warp][d] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t n = *d_count;
-  const uint32_t num_tiles = (n + kSortTileItems - 1) / kSortTileItems;
+  const uint32_t num_tiles = (n + kTileItems - 1) / kTileItems;
   if (tile >= num_tiles) return;
-  const uint32_t tile_base = tile * kSortTileItems;
+  const uint32_t tile_base = tile * kTileItems;
+  GS_TRACE(0);
+  const bool full_tile = tile_base + kTileItems <= n;
 
   // warp-striped load: warp w owns 512 consecutive pairs, item i of lane l is base + i*32 + l
   uint32_t key[kSortKPT], val[kSortKPT];
   const uint32_t wbase = tile_base + warp * (32 * kSortKPT) + lane;
+  if (GATHER) {
 #pragma unroll
-  for (int i = 0; i < kSortKPT; ++i) {
-    uint32_t idx = wbase + i * 32;
-    key[i] = (idx < n) ? __ldg(src_k + idx) : 0xFFFFFFFFu;  // pads sort last (S/SortCommon.hlsl:244-247 does the same)
+    for (int i = 0; i < kSortKPT; ++i) {
+      const uint32_t idx = wbase + i * 32;
+      val[i] = (idx < n) ? __ldg(src_v + idx) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int i = 0; i < kSortKPT; ++i) key[i] = (val[i] != 0xFFFFFFFFu) ? __ldg(src_k + val[i]) : 0xFFFFFFFFu;
+  } else if (full_tile) {
+#pragma unroll
+    for (int i = 0; i < kSortKPT; ++i) key[i] = __ldg(src_k + wbase + i * 32);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kSortKPT; ++i) {
+      const uint32_t idx = wbase + i * 32;
+      key[i] = (idx < n) ? __ldg(src_k + idx) : 0xFFFFFFFFu;  // pads sort last (S/SortCommon.hlsl:244-247 does the same)
+    }
   }
-#pragma unroll
-  for (int i = 0; i < kSortKPT; ++i) {
-    uint32_t idx = wbase + i * 32;
-    val[i] = (idx < n) ? __ldg(src_v + idx) : 0u;
-  }
-#pragma unroll
-  for (int d = lane; d < 256; d += 32) s_whist[warp][d] = 0;
-  __syncwarp();
 
-  // stable in-warp ranking by ballot match
-  uint32_t rank[kSortKPT];
+  // 1. tile digit histogram (cheap, before ranking) so that the LOCAL count is published as early as possible
+#pragma unroll
+  for (int i = 0; i < kSortKPT; ++i) {
+    const uint32_t d = (key[i] >> shift) & (NB - 1);
+    const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+    if (__all_sync(0xffffffffu, d == d0)) {   // skewed digits (high bytes of depth keys): one add per warp
+      if (lane == 0) atomicAdd(&s_hist[d0], 32u);
+    } else {
+      atomicAdd(&s_hist[d], 1u);
+    }
+  }
+  __syncthreads();
+  GS_TRACE(1);
+
+  // 2. publish, then resolve the exclusive prefix over earlier tiles with 4 status probes in flight
+  uint32_t prefix = 0, tile_total = 0;
+  if (tid < NB) {
+    tile_total = s_hist[tid];  // includes pads (only the last digit of the last tile)
+    uint32_t pub = tile_total;
+    if (tid == NB - 1 && !full_tile) pub -= (tile_base + kTileItems - n);
+    volatile uint32_t *lb = lookback + (size_t)tile * NB + tid;
+    if (tile == 0) {
+      *lb = kFlagIncl | pub;
+    } else {
+      *lb = kFlagLocal | pub;
+      int t = (int)tile - 1;
+      bool done = false;
+      while (!done) {   // 8 status probes in flight per round: the window of not-yet-inclusive predecessors is ~rate x RTT tiles
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (t - q >= 0) ? lookback[(size_t)(t - q) * NB + tid] : kFlagIncl;
+        int used = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (!done && used == q) {
+            if (v[q] != 0) {
+              prefix += v[q] & kValMask;
+              used = q + 1;
+              if (v[q] & kFlagIncl) done = true;
+            }
+          }
+        }
+        t -= used;
+      }
+      *lb = kFlagIncl | (prefix + pub);
+    }
+  }
+  GS_TRACE(2);
+  if (!GATHER) {  // payloads: issued now, consumed at the scatter
+    if (full_tile) {
+#pragma unroll
+      for (int i = 0; i < kSortKPT; ++i) val[i] = __ldg(src_v + wbase + i * 32);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSortKPT; ++i) {
+        const uint32_t idx = wbase + i * 32;
+        val[i] = (idx < n) ? __ldg(src_v + idx) : 0u;
+      }
+    }
+  }
+
+  // 3. stable in-warp ranking; ranks (< 4096) are packed two per register
+  uint32_t rank2[kSortKPT / 2];
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < kSortKPT; ++i) {
-    const uint32_t d = (key[i] >> shift) & 255u;
-    uint32_t m = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const bool bit = (d >> b) & 1u;
-      const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-      m &= bit ? bal : ~bal;
-    }
+    const uint32_t d = (key[i] >> shift) & (NB - 1);
+    const uint32_t m = match_digit<BITS>(d);
     const uint32_t leader = __ffs(m) - 1;
     uint32_t prev = 0;
     if (lane == leader) {
@@ -146,87 +242,133 @@ k_onesweep(const uint32_t *__restrict__ src_k, const uint32_t *__restrict__ src_
       s_whist[warp][d] = prev + __popc(m);
     }
     prev = __shfl_sync(0xffffffffu, prev, leader);
-    rank[i] = prev + __popc(m & lt_mask);
+    const uint32_t r = prev + __popc(m & lt_mask);
+    if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
     __syncwarp();
   }
   __syncthreads();
+  GS_TRACE(3);
 
-  // thread `tid` now owns digit `tid`: exclusive prefix over warps, tile total
-  uint32_t run = 0;
+  // 4. thread `tid` < NB owns digit `tid`: exclusive prefix over warps, tile/global digit bases
+  if (tid < NB) {
+    uint32_t run = 0;
 #pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) {
-    uint32_t c = s_whist[w][tid];
-    s_whist[w][tid] = run;
-    run += c;
-  }
-  const uint32_t tile_total = run;  // includes pads (only digit 255 of the last tile)
-  uint32_t pub = tile_total;
-  if (tid == 255 && tile_base + kSortTileItems > n) pub -= (tile_base + kSortTileItems - n);
-
-  // publish early so successors can start their look-back while we scan
-  volatile uint32_t *lb = lookback + (size_t)tile * 256 + tid;
-  if (tile == 0) *lb = kFlagIncl | pub; else *lb = kFlagLocal | pub;
-
-  const uint32_t dig_start = block_excl_scan_256(tile_total, s_scan);
-  const uint32_t gbase = block_excl_scan_256(__ldg(ghist + tid), s_scan);
-
-  uint32_t prefix = 0;
-  if (tile > 0) {
-    int t = (int)tile - 1;
-    while (true) {
-      uint32_t v = lookback[(size_t)t * 256 + tid];
-      if (v == 0) continue;  // predecessor not published yet
-      prefix += v & kValMask;
-      if (v & kFlagIncl) break;
-      --t;
+    for (int w = 0; w < kSortWarps; ++w) {
+      uint32_t c = s_whist[w][tid];
+      s_whist[w][tid] = run;
+      run += c;
     }
-    *lb = kFlagIncl | (prefix + pub);
   }
-  s_dig_start[tid] = dig_start;
-  s_off[tid] = gbase + prefix - dig_start;
+  const uint32_t dig_start = block_excl_scan<kSortWarps>(tile_total, s_scan);
+  const uint32_t gbase = block_excl_scan<kSortWarps>(tid < NB ? __ldg(ghist + tid) : 0u, s_scan);
+  if (tid < NB) {
+    s_dig_start[tid] = dig_start;
+    s_off[tid] = gbase + prefix - dig_start;
+  }
   __syncthreads();
+  GS_TRACE(4);
 
-  // scatter into digit order inside shared memory
+  // 5. scatter into digit order inside shared memory
 #pragma unroll
   for (int i = 0; i < kSortKPT; ++i) {
-    const uint32_t d = (key[i] >> shift) & 255u;
-    const uint32_t pos = s_dig_start[d] + s_whist[warp][d] + rank[i];
-    s_keys[pos] = key[i];
-    s_vals[pos] = val[i];
+    const uint32_t d = (key[i] >> shift) & (NB - 1);
+    const uint32_t r = (i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
+    const uint32_t pos = s_dig_start[d] + s_whist[warp][d] + r;
+    s_kv[pos] = make_uint2(key[i], val[i]);
   }
   __syncthreads();
+  GS_TRACE(5);
 
-  const uint32_t valid = min(kSortTileItems, n - tile_base);
+  const uint32_t valid = full_tile ? kTileItems : n - tile_base;
 #pragma unroll 4
   for (uint32_t j = tid; j < valid; j += kSortThreads) {
-    const uint32_t k = s_keys[j];
-    const uint32_t dst = j + s_off[(k >> shift) & 255u];
-    dst_k[dst] = k;
-    dst_v[dst] = s_vals[j];
+    const uint2 kv = s_kv[j];
+    const uint32_t dst = j + s_off[(kv.x >> shift) & (NB - 1)];
+    dst_k[dst] = kv.x;
+    dst_v[dst] = kv.y;
+  }
+  GS_TRACE(6);
+}
+
+// optional per-tile phase trace of the first pass (debug/profiling aid): GS_SORT_TRACE=<file>
+static uint64_t *g_trace = nullptr;
+static uint32_t g_trace_tiles = 0;
+
+static int sort_threads() {
+  static int v = 0;
+  if (!v) { const char *e = getenv("GS_SORT_THREADS"); v = (e && atoi(e) == 512) ? 512 : 256; }
+  return v;
+}
+
+template <int BITS>
+static void launch_pass(uint32_t tiles, cudaStream_t s, const uint32_t *sk, const uint32_t *sv, uint32_t *dk, uint32_t *dv,
+                        const uint32_t *d_count, int shift, const uint32_t *ghist, uint32_t *lookback, uint32_t *ticket, uint64_t *trace,
+                        bool gather) {
+  auto go = [&](auto kern, int threads) {
+    const size_t smem = (size_t)threads * kSortKPT * 8 + (size_t)(threads / 32) * (1u << BITS) * 4;
+    static thread_local const void *configured[16];
+    static thread_local int nconf = 0;
+    bool seen = false;
+    for (int i = 0; i < nconf; ++i) seen |= configured[i] == (const void *)kern;
+    if (!seen) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (nconf < 16) configured[nconf++] = (const void *)kern;
+    }
+    const uint32_t per = (uint32_t)threads * kSortKPT;
+    const uint32_t grid = (uint32_t)(((uint64_t)tiles * kSortTileItems + per - 1) / per);
+    kern<<<grid, threads, smem, s>>>(sk, sv, dk, dv, d_count, shift, ghist, lookback, ticket, trace);
+  };
+  if (sort_threads() == 512) {
+    if (gather) go(k_onesweep<BITS, true, 512>, 512); else go(k_onesweep<BITS, false, 512>, 512);
+  } else {
+    if (gather) go(k_onesweep<BITS, true, 256>, 256); else go(k_onesweep<BITS, false, 256>, 256);
   }
 }
 
-void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, uint32_t capacity, int passes, bool hist_ready,
-                       const SortScratch &sc, cudaStream_t s, cudaEvent_t *pass_events) {
+void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, uint32_t capacity, int passes, int bits,
+                       bool hist_ready, const SortScratch &sc, cudaStream_t s, cudaEvent_t *pass_events, const uint32_t *key_table) {
   if (capacity == 0) return;
   const uint32_t tiles = (capacity + kSortTileItems - 1) / kSortTileItems;
-  cudaMemsetAsync(sc.lookback, 0, (size_t)tiles * 256 * passes * sizeof(uint32_t), s);
+  const uint32_t nb = 1u << bits;
+  cudaMemsetAsync(sc.lookback, 0, (size_t)tiles * nb * passes * sizeof(uint32_t), s);
   cudaMemsetAsync(sc.tickets, 0, 4 * sizeof(uint32_t), s);
   if (!hist_ready) {
     cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
     const uint32_t grid = min(tiles, 148u * 8u);
-    if (passes == 4) k_sort_hist<4><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
-    else k_sort_hist<2><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
+    if (passes == 4) k_sort_hist<4, 8><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
+    else if (bits == 6) k_sort_hist<2, 6><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
+    else if (bits == 7) k_sort_hist<2, 7><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
+    else k_sort_hist<2, 8><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
   }
   uint32_t *sk = keys, *sv = vals, *dk = sc.alt_keys, *dv = sc.alt_vals;
+  const char *trace_path = getenv("GS_SORT_TRACE");
+  if (trace_path && passes == 4 && g_trace_tiles < tiles) {
+    cudaFree(g_trace);
+    cudaMalloc(&g_trace, (size_t)tiles * 8 * sizeof(uint64_t));
+    g_trace_tiles = tiles;
+  }
   for (int p = 0; p < passes; ++p) {
+    uint64_t *trace = (trace_path && passes == 4 && p == 1) ? g_trace : nullptr;
+    if (trace) cudaMemsetAsync(trace, 0, (size_t)tiles * 8 * sizeof(uint64_t), s);
     if (pass_events) cudaEventRecord(pass_events[p], s);
-    k_onesweep<<<tiles, kSortThreads, 0, s>>>(sk, sv, dk, dv, d_count, 8 * p, sc.ghist + 256 * p,
-                                               sc.lookback + (size_t)p * tiles * 256, sc.tickets + p);
+    uint32_t *lb = sc.lookback + (size_t)p * tiles * nb;
+    const bool gather = key_table != nullptr && p == 0;   // pass 0 reads key_table[vals[i]] instead of keys[i]
+    const uint32_t *src_keys = gather ? key_table : sk;
+    if (bits == 6) launch_pass<6>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
+    else if (bits == 7) launch_pass<7>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
+    else launch_pass<8>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
     uint32_t *t = sk; sk = dk; dk = t;
     t = sv; sv = dv; dv = t;
   }
   if (pass_events) cudaEventRecord(pass_events[passes], s);
+  if (trace_path && passes == 4) {
+    cudaStreamSynchronize(s);
+    uint64_t *h = (uint64_t *)malloc((size_t)tiles * 64);
+    cudaMemcpy(h, g_trace, (size_t)tiles * 64, cudaMemcpyDeviceToHost);
+    FILE *f = fopen(trace_path, "wb");
+    if (f) { fwrite(h, 64, tiles, f); fclose(f); }
+    free(h);
+  }
 }
 
 }  // namespace gs

@@ -9,8 +9,9 @@
 //     fully coalesced 16-byte stores (a 40-byte stride cannot be stored with float4);
 //   * the same kernel emits the splat's screen-tile rectangle (4 bytes) for the binner,
 //     so the raster stage never has to touch the 40-byte record to count tiles;
-//   * CSCalcDistances also accumulates the four 8-bit digit histograms of the keys it
-//     writes, which removes the radix sort's separate histogram read (4 B/splat).
+//   * CSCalcDistances writes the depth keys in natural order (coalesced) and accumulates the four
+//     8-bit digit histograms on the way; the gather through last frame's order is folded into
+//     pass 0 of the radix sort, so neither a histogram read nor a gathered key array exists.
 #include "gs_kernels.cuh"
 
 namespace gs {
@@ -39,25 +40,40 @@ __device__ __forceinline__ float3 load_pos(const AssetView &a, uint32_t idx) {
 
 constexpr int kDistItems = 4;  // keys per thread
 
-__global__ void __launch_bounds__(256) k_calc_distances(AssetView a, float4 row, const uint32_t *__restrict__ order,
-                                                        uint32_t *__restrict__ keys, uint32_t *__restrict__ ghist) {
+// Per-splat depth keys in NATURAL order + the four digit histograms of the sort.  The reference's
+// CSCalcDistances writes key(pos[order[i]]) (S/SplatUtilities.compute:76-81); the multiset of keys -- all the
+// histograms need -- does not depend on the order, and the gather through `order` happens inside pass 0
+// of the radix sort (gs_sort.cu, GATHER), so this kernel is fully coalesced and nothing is gathered twice.
+__global__ void __launch_bounds__(256) k_calc_distances(AssetView a, float4 row, uint32_t *__restrict__ key_table,
+                                                        uint32_t *__restrict__ ghist) {
   __shared__ uint32_t sh[4 * 256];
   for (int i = threadIdx.x; i < 1024; i += 256) sh[i] = 0;
   __syncthreads();
   const uint32_t base = blockIdx.x * (256 * kDistItems);
+  const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
   for (int it = 0; it < kDistItems; ++it) {
-    uint32_t i = base + it * 256 + threadIdx.x;
-    if (i < a.n) {
-      uint32_t o = __ldg(order + i);  // gather through the previous order, S/SplatUtilities.compute:76
-      float3 p = load_pos(a, o);
+    const uint32_t i = base + it * 256 + threadIdx.x;
+    const bool live = i < a.n;
+    uint32_t k = 0;
+    if (live) {
+      float3 p = load_pos(a, i);
       float z = fmaf(row.z, p.z, fmaf(row.y, p.y, fmaf(row.x, p.x, row.w)));
-      uint32_t k = float_to_sortable_uint(z);
-      keys[i] = k;
+      k = float_to_sortable_uint(z);
+      key_table[i] = k;
       atomicAdd(&sh[k & 255u], 1u);
       atomicAdd(&sh[256 + ((k >> 8) & 255u)], 1u);
-      atomicAdd(&sh[512 + ((k >> 16) & 255u)], 1u);
-      atomicAdd(&sh[768 + (k >> 24)], 1u);
+    }
+    // The two high digits are nearly constant inside a warp (Morton-ordered neighbours have similar depth);
+    // plain atomics would serialise 32-way on one bank, so a uniform warp is counted with one add.
+    const uint32_t hi = k >> 16;
+    const uint32_t hi0 = __shfl_sync(0xffffffffu, hi, 0);
+    const uint32_t livemask = __ballot_sync(0xffffffffu, live);
+    if (livemask == 0xffffffffu && __all_sync(0xffffffffu, hi == hi0)) {
+      if (lane == 0) { atomicAdd(&sh[512 + (hi0 & 255u)], 32u); atomicAdd(&sh[768 + (hi0 >> 8)], 32u); }
+    } else if (live) {
+      atomicAdd(&sh[512 + (hi & 255u)], 1u);
+      atomicAdd(&sh[768 + (hi >> 8)], 1u);
     }
   }
   __syncthreads();
@@ -364,12 +380,11 @@ void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s) {
   if (n) k_set_indices<<<(n + 255) / 256, 256, 0, s>>>(order, n);
 }
 
-void launch_calc_distances(const AssetView &a, const FrameConsts &fc, const uint32_t *order, uint32_t *keys, uint32_t *ghist,
-                           cudaStream_t s) {
+void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s) {
   if (!a.n) return;
   const uint32_t per = 256 * kDistItems;
   k_calc_distances<<<(a.n + per - 1) / per, 256, 0, s>>>(a, make_float4(fc.sort_row[0], fc.sort_row[1], fc.sort_row[2], fc.sort_row[3]),
-                                                         order, keys, ghist);
+                                                         key_table, ghist);
 }
 
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
