@@ -161,3 +161,35 @@ def test_error_behaviour(g, ctx):
         r.m_SHOrder = 7
         r.CalcViewData(cam)
     r.Dispose()
+
+
+@pytest.mark.parametrize("count,band", [(2, 1), (3, 2), (4, 1), (8, 1)])
+def test_tile_partition_bands_reassemble_the_full_frame(g, O, ctx, count, band):
+    """SURVEY 8e.1 on one GPU: render every partition band-packed, all-gather by hand, gs_unshuffle_bands == full frame."""
+    import ctypes as C
+    import torch
+    from unitygaussiansplatting_b200 import _native as N
+    from unitygaussiansplatting_b200.multigpu import BandPartition, TILE, unshuffle
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 30000, 0x5EED0007, "Medium")
+    cam = camera(g, 333, 211)
+    r = g.GaussianSplatRenderer(asset, ctx)
+    full = np.zeros((211, 333, 4), np.float16)
+    r.SortAndRenderSplats(cam, rt=full)
+    parts = [BandPartition(211, count, i, band) for i in range(count)]
+    gathered = torch.zeros((count, parts[0].rows_per_partition, 333, 4), dtype=torch.float16, device="cuda")
+    for p in parts:
+        r.partition, r.band_packed = p.options(), True
+        own_px = p.own_tile_rows() * TILE
+        if own_px:
+            r.SortAndRenderSplats(cam, rt=gathered[p.index][:own_px])
+    ctx.sync()
+    out = torch.zeros((211, 333, 4), dtype=torch.float16, device="cuda")
+    unshuffle(ctx, gathered, parts[0], out)
+    ctx.sync()
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), full)
+    # host-image variant of the same call
+    host = np.zeros((211, 333, 4), np.float16)
+    unshuffle(ctx, gathered, parts[0], host)
+    assert np.array_equal(host, full)
+    r.Dispose()

@@ -261,7 +261,7 @@ static int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const G
   rec(ctx, EV_BIN1);
   launch_raster(fc, opt, as->view, ctx->bin, d_rt, pitch, fmt, nullptr, ctx->stream);
   rec(ctx, EV_RASTER1);
-  ctx->launches += 1 + 3 + 1;  // bin_emit, sort (hist + 2 passes), raster
+  ctx->launches += 1 + 2 + 1;  // bin_emit, 2 sort passes, raster
   GS_CUDA_TRY(ctx, cudaGetLastError());
   return GS_OK;
 }

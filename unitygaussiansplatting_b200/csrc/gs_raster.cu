@@ -51,61 +51,67 @@ __device__ __forceinline__ uint32_t rect_entries(uint32_t r, const Partition &p)
   return rows * (x1 - x0 + 1);
 }
 
-constexpr int kBinItems = 4;
-constexpr int kBinBlock = 256 * kBinItems;
+constexpr int kBinItems = 8;                  // ranks per thread
+constexpr int kBinBlock = 256 * kBinItems;    // ranks per block
 
 // ---- 1. count + scan + emit in ONE pass ---------------------------------------------------------
 // Blocks take their index by atomic ticket, publish their entry total with a LOCAL flag, resolve
 // their exclusive offset by a warp-parallel decoupled look-back (32 predecessors per probe), then
-// emit (tile id, splat id) entries in depth order.
+// emit (tile id, splat id) entries in depth order.  Emission is warp-cooperative: the 32 ranks a warp
+// holds for one item slot own one contiguous output range; lane x of the warp writes entry x of that
+// range (owner found by a 5-step shuffle search over the lanes' prefix sums), so every store is a
+// full coalesced line regardless of how many tiles each splat touches.
 enum : uint32_t { kBinFlagLocal = 1u << 30, kBinFlagIncl = 2u << 30, kBinValMask = (1u << 30) - 1u };
 
-__device__ __forceinline__ void emit_entry(uint32_t e, uint32_t r, uint32_t id, uint32_t off, const Partition &p, uint32_t tilesX,
-                                           uint32_t capacity, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+__device__ __forceinline__ uint32_t entry_tile(uint32_t e, uint32_t r, const Partition &p, uint32_t tilesX) {
   const uint32_t x0 = r & 255u, y0 = (r >> 8) & 255u, x1 = (r >> 16) & 255u;
   const uint32_t w = x1 - x0 + 1;
-  const uint32_t krow = e / w, tx = x0 + (e - krow * w);
-  const uint32_t ty = p.kth_own_row(p.own_rows_below(y0) + krow);
-  const uint32_t o = off + e;
-  if (o < capacity) {
-    keys[o] = ty * tilesX + tx;
-    vals[o] = id;
-  }
+  uint32_t krow = 0, col = e;
+  if (e >= w) { krow = e / w; col = e - krow * w; }
+  const uint32_t ty = p.count <= 1 ? y0 + krow : p.kth_own_row(p.own_rows_below(y0) + krow);
+  return ty * tilesX + x0 + col;
 }
 
 __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ order, const uint32_t *__restrict__ rect, uint32_t n,
                                                   Partition part, uint32_t tilesX, volatile uint32_t *status, uint32_t *ticket,
                                                   uint32_t nblocks, uint32_t capacity, uint32_t *__restrict__ keys,
-                                                  uint32_t *__restrict__ vals, uint32_t *__restrict__ entry_count) {
+                                                  uint32_t *__restrict__ vals, uint32_t *__restrict__ entry_count,
+                                                  uint32_t *__restrict__ ghist, uint32_t digit_bits) {
   __shared__ uint32_t s_w[8];
   __shared__ uint32_t s_block, s_excl;
+  __shared__ uint32_t s_dh[512];   // digit histograms of the two sort passes over the tile ids we emit
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
+  s_dh[threadIdx.x] = 0; s_dh[threadIdx.x + 256] = 0;
+  const uint32_t dmask = (1u << digit_bits) - 1u;
   __syncthreads();
   const uint32_t b = s_block;
-  const uint32_t base = b * kBinBlock + threadIdx.x * kBinItems;
-  uint32_t id[kBinItems], rc[kBinItems], cnt[kBinItems], sum = 0;
+  // warp-striped ranks: item i of lane l is rank wbase + i*32 + l (coalesced loads, and the 32 lanes of one
+  // item slot hold 32 consecutive ranks == one contiguous output range)
+  const uint32_t wbase = b * kBinBlock + warp * (32 * kBinItems) + lane;
+  uint32_t id[kBinItems], rc[kBinItems], pre[kBinItems];
 #pragma unroll
   for (int i = 0; i < kBinItems; ++i) {
-    uint32_t r = base + i;
-    id[i] = 0; rc[i] = kRectEmpty; cnt[i] = 0;
-    if (r < n) id[i] = __ldg(order + r);
+    const uint32_t r = wbase + i * 32;
+    id[i] = (r < n) ? __ldg(order + r) : 0xFFFFFFFFu;
   }
 #pragma unroll
+  for (int i = 0; i < kBinItems; ++i) rc[i] = (id[i] != 0xFFFFFFFFu) ? __ldg(rect + id[i]) : kRectEmpty;
+  uint32_t wtot[kBinItems], wsum = 0;
+#pragma unroll
   for (int i = 0; i < kBinItems; ++i) {
-    if (base + i < n) {
-      rc[i] = __ldg(rect + id[i]);
-      cnt[i] = rect_entries(rc[i], part);
+    const uint32_t c = rect_entries(rc[i], part);
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (uint32_t)o) inc += t;
     }
-    sum += cnt[i];
+    pre[i] = inc - c;
+    wtot[i] = __shfl_sync(0xffffffffu, inc, 31);
+    wsum += wtot[i];
   }
-  uint32_t inc = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= (uint32_t)o) inc += t;
-  }
-  if (lane == 31) s_w[warp] = inc;
+  if (lane == 0) s_w[warp] = wsum;
   __syncthreads();
   uint32_t woff = 0, total = 0;
 #pragma unroll
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
         const int idx = top - (int)lane;
         uint32_t v;
         do {
-          v = idx >= 0 ? status[idx] : kBinFlagIncl;
+          v = idx >= 0 ? status[idx] : (uint32_t)kBinFlagIncl;
         } while (__any_sync(0xffffffffu, v == 0));
         const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v & kBinFlagIncl) != 0);
         const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;   // nearest predecessor that is already inclusive
@@ -147,22 +153,38 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
     }
   }
   __syncthreads();
-  uint32_t off = s_excl + woff + inc - sum;
+  uint32_t off = s_excl + woff;
 #pragma unroll
   for (int i = 0; i < kBinItems; ++i) {
-    // small footprints: the owning lane writes them; large ones are spread over the warp
-    const bool big = cnt[i] > 8;
-    if (!big)
-      for (uint32_t e = 0; e < cnt[i]; ++e) emit_entry(e, rc[i], id[i], off, part, tilesX, capacity, keys, vals);
-    uint32_t bigmask = __ballot_sync(0xffffffffu, big);
-    while (bigmask) {
-      const int src = __ffs(bigmask) - 1;
-      bigmask &= bigmask - 1;
-      const uint32_t c = __shfl_sync(0xffffffffu, cnt[i], src), r = __shfl_sync(0xffffffffu, rc[i], src),
-                     d = __shfl_sync(0xffffffffu, id[i], src), o = __shfl_sync(0xffffffffu, off, src);
-      for (uint32_t e = lane; e < c; e += 32) emit_entry(e, r, d, o, part, tilesX, capacity, keys, vals);
+    const uint32_t T = wtot[i];
+    for (uint32_t e0 = 0; e0 < T; e0 += 32) {
+      const uint32_t x = e0 + lane;
+      // owner = last lane whose exclusive prefix is <= x
+      uint32_t lo = 0, hi = 31;
+#pragma unroll
+      for (int step = 0; step < 5; ++step) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        const uint32_t pm = __shfl_sync(0xffffffffu, pre[i], mid);
+        if (pm <= x) lo = mid; else hi = mid - 1;
+      }
+      const uint32_t opre = __shfl_sync(0xffffffffu, pre[i], lo);
+      const uint32_t orc = __shfl_sync(0xffffffffu, rc[i], lo);
+      const uint32_t oid = __shfl_sync(0xffffffffu, id[i], lo);
+      const uint32_t o = off + x;
+      if (x < T && o < capacity) {
+        const uint32_t tile = entry_tile(x - opre, orc, part, tilesX);
+        keys[o] = tile;
+        vals[o] = oid;
+        atomicAdd(&s_dh[tile & dmask], 1u);
+        atomicAdd(&s_dh[256 + ((tile >> digit_bits) & dmask)], 1u);
+      }
     }
-    off += cnt[i];
+    off += T;
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < 512; i += 256) {
+    const uint32_t c = s_dh[i];
+    if (c) atomicAdd(&ghist[i], c);
   }
 }
 
@@ -175,9 +197,11 @@ void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t 
   if (!n) { cudaMemsetAsync(bs.entry_count, 0, 16, s); return; }
   const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
   cudaMemsetAsync(bs.block_sums, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
+  const int bits = bin_sort_bits(tiles);
+  cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
   k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, n, part, fc.tilesX, bs.block_sums + 1, bs.block_sums, nblocks, bs.capacity,
-                                     bs.tile_keys, bs.tile_vals, bs.entry_count);
-  launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, 2, bin_sort_bits(tiles), false, sc, s);
+                                     bs.tile_keys, bs.tile_vals, bs.entry_count, sc.ghist, (uint32_t)bits);
+  launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, 2, bits, true, sc, s);
 }
 
 // ---- 2. raster ---------------------------------------------------------------------------------
@@ -264,6 +288,8 @@ k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, cons
 
     const uint32_t cnt = min(256u, range.y - base);
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+      // a warp whose 32 pixels all reached dst.a == 1 ignores everything behind exactly: skip the batch remainder
+      if (__all_sync(0xffffffffu, d3 == 1.0f || !in_image)) break;
       // one ballot culls 32 splats against this warp's 8x4 pixel block
       const uint32_t e = c0 + lane;
       bool hit = false;

@@ -38,7 +38,7 @@ __device__ __forceinline__ float3 load_pos(const AssetView &a, uint32_t idx) {
   return p;
 }
 
-constexpr int kDistItems = 4;  // keys per thread
+constexpr int kDistItems = 4;  // keys per thread: 4 CONSECUTIVE splats, so Norm11 / Float32 positions come in as 16-byte vectors
 
 // Per-splat depth keys in NATURAL order + the four digit histograms of the sort.  The reference's
 // CSCalcDistances writes key(pos[order[i]]) (S/SplatUtilities.compute:76-81); the multiset of keys -- all the
@@ -49,24 +49,59 @@ __global__ void __launch_bounds__(256) k_calc_distances(AssetView a, float4 row,
   __shared__ uint32_t sh[4 * 256];
   for (int i = threadIdx.x; i < 1024; i += 256) sh[i] = 0;
   __syncthreads();
-  const uint32_t base = blockIdx.x * (256 * kDistItems);
   const uint32_t lane = threadIdx.x & 31;
+  // persistent CTAs: the shared histograms are flushed to the 1024 global counters once per CTA, not once per
+  // 1024 splats (6M same-address L2 atomics were the whole cost of this kernel)
+  for (uint32_t tile = blockIdx.x; tile * (256u * kDistItems) < a.n; tile += gridDim.x) {
+  const uint32_t first = (tile * 256 + threadIdx.x) * kDistItems;   // multiple of 4: the 4 splats share a chunk
+  float3 p[kDistItems];
+  const bool full = first + kDistItems <= a.n;
+  if (full && a.posFmt == 2) {          // Norm11: 4 x 4 bytes
+    const uint4 e = __ldg(reinterpret_cast<const uint4 *>(a.pos) + (first >> 2));
+    p[0] = dec_11_10_11(e.x); p[1] = dec_11_10_11(e.y); p[2] = dec_11_10_11(e.z); p[3] = dec_11_10_11(e.w);
+  } else if (full && a.posFmt == 0) {   // Float32: 4 x 12 bytes = 3 vectors
+    const uint4 *q = reinterpret_cast<const uint4 *>(a.pos) + (size_t)(first >> 2) * 3;
+    const uint4 e0 = __ldg(q), e1 = __ldg(q + 1), e2 = __ldg(q + 2);
+    p[0] = make_float3(__uint_as_float(e0.x), __uint_as_float(e0.y), __uint_as_float(e0.z));
+    p[1] = make_float3(__uint_as_float(e0.w), __uint_as_float(e1.x), __uint_as_float(e1.y));
+    p[2] = make_float3(__uint_as_float(e1.z), __uint_as_float(e1.w), __uint_as_float(e2.x));
+    p[3] = make_float3(__uint_as_float(e2.y), __uint_as_float(e2.z), __uint_as_float(e2.w));
+  } else {
+#pragma unroll
+    for (int it = 0; it < kDistItems; ++it)
+      p[it] = (first + it < a.n) ? load_vector(a.pos, (uint64_t)(first + it) * vec_stride(a.posFmt), a.posFmt) : make_float3(0.f, 0.f, 0.f);
+  }
+  const uint32_t ci = first >> 8;
+  if (ci < a.chunkCount) {  // LoadSplatPos, S/GaussianSplatting.hlsl:409-421
+    const float4 *c = reinterpret_cast<const float4 *>(a.chunks + ci);
+    const float4 px_py = __ldg(c + 1);
+    const float2 pz = __ldg(reinterpret_cast<const float2 *>(c + 2));
+#pragma unroll
+    for (int it = 0; it < kDistItems; ++it) {
+      p[it].x = lerpf(px_py.x, px_py.y, p[it].x);
+      p[it].y = lerpf(px_py.z, px_py.w, p[it].y);
+      p[it].z = lerpf(pz.x, pz.y, p[it].z);
+    }
+  }
+  uint32_t k[kDistItems];
+#pragma unroll
+  for (int it = 0; it < kDistItems; ++it) k[it] = float_to_sortable_uint(fmaf(row.z, p[it].z, fmaf(row.y, p[it].y, fmaf(row.x, p[it].x, row.w))));
+  if (full) {
+    reinterpret_cast<uint4 *>(key_table)[first >> 2] = make_uint4(k[0], k[1], k[2], k[3]);
+  } else {
+    for (int it = 0; it < kDistItems; ++it)
+      if (first + it < a.n) key_table[first + it] = k[it];
+  }
 #pragma unroll
   for (int it = 0; it < kDistItems; ++it) {
-    const uint32_t i = base + it * 256 + threadIdx.x;
-    const bool live = i < a.n;
-    uint32_t k = 0;
+    const bool live = first + it < a.n;
     if (live) {
-      float3 p = load_pos(a, i);
-      float z = fmaf(row.z, p.z, fmaf(row.y, p.y, fmaf(row.x, p.x, row.w)));
-      k = float_to_sortable_uint(z);
-      key_table[i] = k;
-      atomicAdd(&sh[k & 255u], 1u);
-      atomicAdd(&sh[256 + ((k >> 8) & 255u)], 1u);
+      atomicAdd(&sh[k[it] & 255u], 1u);
+      atomicAdd(&sh[256 + ((k[it] >> 8) & 255u)], 1u);
     }
     // The two high digits are nearly constant inside a warp (Morton-ordered neighbours have similar depth);
     // plain atomics would serialise 32-way on one bank, so a uniform warp is counted with one add.
-    const uint32_t hi = k >> 16;
+    const uint32_t hi = k[it] >> 16;
     const uint32_t hi0 = __shfl_sync(0xffffffffu, hi, 0);
     const uint32_t livemask = __ballot_sync(0xffffffffu, live);
     if (livemask == 0xffffffffu && __all_sync(0xffffffffu, hi == hi0)) {
@@ -76,6 +111,7 @@ __global__ void __launch_bounds__(256) k_calc_distances(AssetView a, float4 row,
       atomicAdd(&sh[768 + (hi >> 8)], 1u);
     }
   }
+  }  // tile loop
   __syncthreads();
   for (int i = threadIdx.x; i < 1024; i += 256) {
     uint32_t c = sh[i];
@@ -383,7 +419,8 @@ void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s) {
 void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s) {
   if (!a.n) return;
   const uint32_t per = 256 * kDistItems;
-  k_calc_distances<<<(a.n + per - 1) / per, 256, 0, s>>>(a, make_float4(fc.sort_row[0], fc.sort_row[1], fc.sort_row[2], fc.sort_row[3]),
+  const uint32_t tiles = (a.n + per - 1) / per;
+  k_calc_distances<<<tiles < 148u * 8u ? tiles : 148u * 8u, 256, 0, s>>>(a, make_float4(fc.sort_row[0], fc.sort_row[1], fc.sort_row[2], fc.sort_row[3]),
                                                          key_table, ghist);
 }
 
