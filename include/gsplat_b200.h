@@ -181,7 +181,10 @@ GS_API int gs_composite(GsContext *ctx, const GsImage *rt, GsImage *camera_targe
  * (do_sort ? gs_sort : nothing) -> gs_calc_view -> gs_render [-> gs_composite if
  * camera_target != NULL].  do_sort == (m_FrameCounter % m_SortNthFrame == 0),
  * R/GaussianSplatRenderer.cs:120-121.  rt may be NULL when camera_target is given
- * (the RT then lives only in library scratch). */
+ * (the RT then lives only in library scratch).
+ * The fused path treats the colour of a splat that cannot produce a fragment (quad off screen, or
+ * opacity below the 1/255 discard) as dead code: its _SplatViewData record keeps pos/axes exactly and
+ * gets colour = 0.  Pixels are unaffected; call gs_calc_view for the complete buffer. */
 GS_API int gs_frame(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp,
                     const GsRenderOptions *opt, int do_sort, GsImage *rt, GsImage *camera_target);
 

@@ -33,6 +33,7 @@ def test_cuda_path_reproduces_golden(g, ctx, name):
     r.SortAndRenderSplats(camera(g, w, h, pos=pos), rt=rt, camera_target=tgt)
     assert np.array_equal(r.readback_keys(), want["keys"])
     assert np.array_equal(r.readback_order(), want["order"])
+    r.CalcViewData(camera(g, w, h, pos=pos))
     assert np.array_equal(r.readback_view(), want["view"])
     assert np.abs(rt.astype(np.float32) - want["rt"].astype(np.float32)).max() <= 1e-3
     assert np.array_equal(rt, want["rt"])

@@ -23,7 +23,13 @@ def _frame_pair(g, O, ctx, asset, cam, blend=0, prev_order=None, **knobs):
     fp, _keep = g.make_frame_params(cam, r.localToWorldMatrix, r.m_SplatScale, r.m_OpacityScale, r.m_SHOrder, r.m_SHOnly,
                                     r.m_Cutouts, r.m_DeletedBits, asset.splatCount)
     ref = O.frame(asset, fp, prev_order=prev_order, blend_mode=blend, threads=O.max_threads())
+    fused_view = r.readback_view()
+    r.CalcViewData(cam)      # the stand-alone entry point writes every record in full (gs_frame skips colour of undrawable splats)
     got = {"keys": r.readback_keys(), "order": r.readback_order(), "view": r.readback_view(), "rt": rt.astype(np.float32)}
+    # fused-frame records: pos/axes always exact; colour exact, or zero for a splat that cannot produce a fragment
+    assert np.array_equal(fused_view[:, :8], ref["view"][:, :8])
+    czero = (fused_view[:, 8:] == 0).all(axis=1)
+    assert np.array_equal(fused_view[~czero, 8:], ref["view"][~czero, 8:])
     r.Dispose()
     return got, ref
 

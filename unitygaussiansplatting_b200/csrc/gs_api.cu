@@ -237,11 +237,11 @@ static int do_sort(GsContext *ctx, GsAsset *as, const FrameConsts &fc) {
   return GS_OK;
 }
 
-static int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameConsts &fc) {
+static int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameConsts &fc, bool cull) {
   int rc = upload_frame_inputs(ctx, as, fp);
   if (rc) return rc;
   rec(ctx, EV_VIEW0);
-  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, ctx->stream);
+  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, cull, ctx->stream);
   rec(ctx, EV_VIEW1);
   ctx->launches += 1;
   as->view_valid = true;
@@ -459,7 +459,7 @@ int gs_calc_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
   if (rc) return rc;
   for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
   FrameConsts fc = make_frame_consts(fp);
-  return do_view(ctx, as, fp, fc);
+  return do_view(ctx, as, fp, fc, false);
 }
 
 int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRenderOptions *opt_in, GsImage *rt) {
@@ -535,7 +535,7 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
   if (rt) { if ((rc = image_ok(ctx, rt, W, H, &rt_pitch))) return rc; rt_fmt = rt->format; }
   for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
   if (do_sort_flag && (rc = do_sort(ctx, as, fc))) return rc;
-  if ((rc = do_view(ctx, as, fp, fc))) return rc;
+  if ((rc = do_view(ctx, as, fp, fc, true))) return rc;   // fused frame: colour of never-drawn splats is dead code
   void *d_rt;
   uint32_t d_pitch;
   const bool rt_dev = rt && rt->memory == GS_MEM_DEVICE;

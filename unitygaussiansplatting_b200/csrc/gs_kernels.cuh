@@ -52,7 +52,7 @@ __device__ __forceinline__ uint32_t footprint_tile_rect(const SplatFootprint &fp
 void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s);
 void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s);
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                      uint32_t *rect, cudaStream_t s);
+                      uint32_t *rect, bool cull_undrawable, cudaStream_t s);
 
 // Radix sort (gs_sort.cu).  Scratch layout is owned by the caller (gs_api.cu).
 struct SortScratch {

@@ -197,7 +197,11 @@ __device__ __forceinline__ float3 operator+(float3 a, float3 b) { return make_fl
 __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 neg(float3 a) { return make_float3(-a.x, -a.y, -a.z); }
 
-template <int SHFMT>
+// CULL (used by the fused gs_frame): a splat whose quad cannot touch the screen, or whose opacity can never reach the
+// 1/255 discard threshold, is never drawn, so its colour half of the record (SH fetch + ShadeSH, 2/3 of the bytes and
+// ~half of the arithmetic) is dead code; the record then carries pos/axes exactly and colour = 0.  gs_calc_view (the
+// stand-alone entry point) always runs the full kernel, so _SplatViewData parity is checked on that one.
+template <int SHFMT, bool CULL>
 __global__ void __launch_bounds__(256)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
             uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out) {
@@ -248,8 +252,8 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
       if (qi == 2) rot = make_float4(x, y, w, z);
     }
     // colour texel (Morton-swizzled 2048-wide image), :423-426
-    float4 col;
-    {
+    float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_color = [&]() {
       const uint32_t ti = splat_index_to_texel(idx);
       if (a.colFmt == 0) {
         col = __ldg(reinterpret_cast<const float4 *>(a.color) + ti);
@@ -261,10 +265,13 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
         col = make_float4(__fdiv_rn((float)(e & 255u), 255.0f), __fdiv_rn((float)((e >> 8) & 255u), 255.0f),
                           __fdiv_rn((float)((e >> 16) & 255u), 255.0f), __fdiv_rn((float)(e >> 24), 255.0f));
       }
-    }
+    };
     ShRaw<SHFMT> shr;
     constexpr uint32_t shStride = SHFMT == 0 ? 192u : SHFMT == 1 ? 96u : SHFMT == 2 ? 60u : 32u;
-    if (fc.shOrder >= 1) shr.load(a.sh + (uint64_t)idx * shStride);
+    if (!CULL) {
+      load_color();
+      if (fc.shOrder >= 1) shr.load(a.sh + (uint64_t)idx * shStride);
+    }
 
     float3 shMin = make_float3(0.f, 0.f, 0.f), shMax = make_float3(1.f, 1.f, 1.f);
     if (chunked) {  // :565-603
@@ -277,19 +284,23 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
       scale.x *= scale.x; scale.x *= scale.x; scale.x *= scale.x;
       scale.y *= scale.y; scale.y *= scale.y; scale.y *= scale.y;
       scale.z *= scale.z; scale.z *= scale.z; scale.z *= scale.z;
-      col.x = lerpf(f16lo(s_chunk.colR), f16hi(s_chunk.colR), col.x);
-      col.y = lerpf(f16lo(s_chunk.colG), f16hi(s_chunk.colG), col.y);
-      col.z = lerpf(f16lo(s_chunk.colB), f16hi(s_chunk.colB), col.z);
-      col.w = lerpf(f16lo(s_chunk.colA), f16hi(s_chunk.colA), col.w);
-      {  // InvSquareCentered01, :5-11
+      shMin = make_float3(f16lo(s_chunk.shR), f16lo(s_chunk.shG), f16lo(s_chunk.shB));
+      shMax = make_float3(f16hi(s_chunk.shR), f16hi(s_chunk.shG), f16hi(s_chunk.shB));
+    }
+    auto finish_color = [&]() {  // chunk un-lerp of colour + opacity, :573-583
+      if (chunked) {
+        col.x = lerpf(f16lo(s_chunk.colR), f16hi(s_chunk.colR), col.x);
+        col.y = lerpf(f16lo(s_chunk.colG), f16hi(s_chunk.colG), col.y);
+        col.z = lerpf(f16lo(s_chunk.colB), f16hi(s_chunk.colB), col.z);
+        col.w = lerpf(f16lo(s_chunk.colA), f16hi(s_chunk.colA), col.w);
+        // InvSquareCentered01, :5-11
         float x = col.w - 0.5f;
         x *= 0.5f;
         float sg = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
         col.w = sqrtf(fabsf(x)) * sg + 0.5f;
       }
-      shMin = make_float3(f16lo(s_chunk.shR), f16lo(s_chunk.shG), f16lo(s_chunk.shB));
-      shMax = make_float3(f16hi(s_chunk.shR), f16hi(s_chunk.shG), f16hi(s_chunk.shB));
-    }
+    };
+    if (!CULL) finish_color();
     const bool shLerp = chunked && SHFMT != 0;  // shFormat > FLOAT32 && <= NORM6, :585
     auto SH = [&](int j) -> float3 {
       float3 v = shr.get(j - 1);
@@ -360,36 +371,52 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
       float l1 = fminf(sqrtf(2.0f * lambda1), 4096.0f), l2 = fminf(sqrtf(2.0f * lambda2), 4096.0f);
       float a1x = l1 * dvx, a1y = l1 * dvy, a2x = l2 * dvy, a2y = l2 * -dvx;
       vw[4] = __float_as_uint(a1x); vw[5] = __float_as_uint(a1y); vw[6] = __float_as_uint(a2x); vw[7] = __float_as_uint(a2y);
-      // colour: ShadeSH(objViewDir), :240-248 + S/GaussianSplatting.hlsl:139-179
-      float wx = fc.cam_pos[0] - cw.x, wy = fc.cam_pos[1] - cw.y, wz = fc.cam_pos[2] - cw.z;
-      float ox = fmaf(fc.w2o[2], wz, fmaf(fc.w2o[1], wy, fc.w2o[0] * wx));
-      float oy = fmaf(fc.w2o[5], wz, fmaf(fc.w2o[4], wy, fc.w2o[3] * wx));
-      float oz = fmaf(fc.w2o[8], wz, fmaf(fc.w2o[7], wy, fc.w2o[6] * wx));
-      float ol = sqrtf(ox * ox + oy * oy + oz * oz);
-      ox = __fdiv_rn(ox, ol); oy = __fdiv_rn(oy, ol); oz = __fdiv_rn(oz, ol);
-      const float dx = ox * -1.0f, dy = oy * -1.0f, dz = oz * -1.0f;  // dir *= -1
-      float3 res = fc.shOnly ? make_float3(0.5f, 0.5f, 0.5f) : make_float3(col.x, col.y, col.z);
-      if (fc.shOrder >= 1) {
-        const float SH_C1 = 0.4886025f;
-        res = res + SH_C1 * (neg(SH(1)) * dy + SH(2) * dz - SH(3) * dx);
-        if (fc.shOrder >= 2) {
-          const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
-          res = res + ((1.0925484f * xy) * SH(4) + (-1.0925484f * yz) * SH(5) + (0.3153916f * (2.0f * zz - xx - yy)) * SH(6) +
-                       (-1.0925484f * xz) * SH(7) + (0.5462742f * (xx - yy)) * SH(8));
-          if (fc.shOrder >= 3) {
-            res = res + ((-0.5900436f * dy * (3.0f * xx - yy)) * SH(9) + (2.8906114f * xy * dz) * SH(10) +
-                         (-0.4570458f * dy * (4.0f * zz - xx - yy)) * SH(11) + (0.3731763f * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy)) * SH(12) +
-                         (-0.4570458f * dx * (4.0f * zz - xx - yy)) * SH(13) + (1.4453057f * dz * (xx - yy)) * SH(14) +
-                         (-0.5900436f * dx * (xx - 3.0f * yy)) * SH(15));
-          }
+      bool drawable = true;
+      if (CULL) {
+        // can the +-2 quad touch a pixel centre at all?  (65000 = the largest opacity CSCalcViewData can emit: the
+        // visible part is then the whole quad; a smaller opacity only shrinks it)
+        SplatFootprint g0;
+        drawable = splat_footprint(clip, a1x, a1y, a2x, a2y, 65000.0f, fc.screenW, fc.screenH, g0) && footprint_tile_rect(g0, fc) != kRectEmpty;
+        if (drawable) {
+          load_color();
+          finish_color();
+          // alpha = sat(exp_neg(..) * half(min(opacity*scale, 65000))) stays below 1/255 when the half is below 0.00392
+          drawable = __half2float(__float2half_rn(fminf(col.w * fc.opacityScale, 65000.0f))) >= 0.00392f;
+          if (drawable && fc.shOrder >= 1) shr.load(a.sh + (uint64_t)idx * shStride);
         }
       }
-      res.x = (res.x > 0.0f) ? res.x : 0.0f; res.y = (res.y > 0.0f) ? res.y : 0.0f; res.z = (res.z > 0.0f) ? res.z : 0.0f;
-      float alpha = fminf(col.w * fc.opacityScale, 65000.0f);
-      vw[8] = (f32tof16(res.x) << 16) | f32tof16(res.y);
-      vw[9] = (f32tof16(res.z) << 16) | f32tof16(alpha);
+      if (drawable) {
+      // colour: ShadeSH(objViewDir), :240-248 + S/GaussianSplatting.hlsl:139-179
+        float wx = fc.cam_pos[0] - cw.x, wy = fc.cam_pos[1] - cw.y, wz = fc.cam_pos[2] - cw.z;
+        float ox = fmaf(fc.w2o[2], wz, fmaf(fc.w2o[1], wy, fc.w2o[0] * wx));
+        float oy = fmaf(fc.w2o[5], wz, fmaf(fc.w2o[4], wy, fc.w2o[3] * wx));
+        float oz = fmaf(fc.w2o[8], wz, fmaf(fc.w2o[7], wy, fc.w2o[6] * wx));
+        float ol = sqrtf(ox * ox + oy * oy + oz * oz);
+        ox = __fdiv_rn(ox, ol); oy = __fdiv_rn(oy, ol); oz = __fdiv_rn(oz, ol);
+        const float dx = ox * -1.0f, dy = oy * -1.0f, dz = oz * -1.0f;  // dir *= -1
+        float3 res = fc.shOnly ? make_float3(0.5f, 0.5f, 0.5f) : make_float3(col.x, col.y, col.z);
+        if (fc.shOrder >= 1) {
+          const float SH_C1 = 0.4886025f;
+          res = res + SH_C1 * (neg(SH(1)) * dy + SH(2) * dz - SH(3) * dx);
+          if (fc.shOrder >= 2) {
+            const float xx = dx * dx, yy = dy * dy, zz = dz * dz, xy = dx * dy, yz = dy * dz, xz = dx * dz;
+            res = res + ((1.0925484f * xy) * SH(4) + (-1.0925484f * yz) * SH(5) + (0.3153916f * (2.0f * zz - xx - yy)) * SH(6) +
+                         (-1.0925484f * xz) * SH(7) + (0.5462742f * (xx - yy)) * SH(8));
+            if (fc.shOrder >= 3) {
+              res = res + ((-0.5900436f * dy * (3.0f * xx - yy)) * SH(9) + (2.8906114f * xy * dz) * SH(10) +
+                           (-0.4570458f * dy * (4.0f * zz - xx - yy)) * SH(11) + (0.3731763f * dz * (2.0f * zz - 3.0f * xx - 3.0f * yy)) * SH(12) +
+                           (-0.4570458f * dx * (4.0f * zz - xx - yy)) * SH(13) + (1.4453057f * dz * (xx - yy)) * SH(14) +
+                           (-0.5900436f * dx * (xx - 3.0f * yy)) * SH(15));
+            }
+          }
+        }
+        res.x = (res.x > 0.0f) ? res.x : 0.0f; res.y = (res.y > 0.0f) ? res.y : 0.0f; res.z = (res.z > 0.0f) ? res.z : 0.0f;
+        float alpha = fminf(col.w * fc.opacityScale, 65000.0f);
+        vw[8] = (f32tof16(res.x) << 16) | f32tof16(res.y);
+        vw[9] = (f32tof16(res.z) << 16) | f32tof16(alpha);
+      }
       SplatFootprint fp;
-      if (splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp))
+      if (drawable && splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp))
         rect = footprint_tile_rect(fp, fc);
     }
     rect_out[idx] = rect;
@@ -424,16 +451,23 @@ void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *
                                                          key_table, ghist);
 }
 
-void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                      uint32_t *rect, cudaStream_t s) {
-  if (!a.n) return;
+template <bool CULL>
+static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
+                               uint32_t *rect, cudaStream_t s) {
   const uint32_t grid = (a.n + 255) / 256;
   switch (a.shFmt) {
-    case 0: k_calc_view<0><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
-    case 1: k_calc_view<1><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
-    case 2: k_calc_view<2><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
-    default: k_calc_view<3><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
+    case 0: k_calc_view<0, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
+    case 1: k_calc_view<1, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
+    case 2: k_calc_view<2, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
+    default: k_calc_view<3, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
   }
+}
+
+void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
+                      uint32_t *rect, bool cull_undrawable, cudaStream_t s) {
+  if (!a.n) return;
+  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, view, rect, s);
+  else launch_calc_view_t<false>(a, fc, cutouts, deleted, view, rect, s);
 }
 
 }  // namespace gs
