@@ -277,8 +277,11 @@ def main():
     roofline = None
     if sort_pass:
         ach = N_SPLATS * SORT_BYTES_PER_PAIR_PASS / (sort_pass * 1e-3) / 1e9
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of k_onesweep<8,0,256>, mean of 3 launches, from the ncu --set full
+        # capture summarised in profiles/r01c_after_rework.md (51.3 + 6.8 MB).  It is BELOW the algorithmic 98 MB because the
+        # ping-pong buffers (2 x 49 MB) mostly stay in the 126 MB L2 between passes.
         roofline = {"kernel": "k_onesweep (one 8-bit digit pass of the radix sort, 4 launches per frame)", "bound": "hbm",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 58.1e6,
                     "algorithmic_bytes_per_launch": N_SPLATS * SORT_BYTES_PER_PAIR_PASS, "launch_ms": sort_pass, "peak_source": peak_src}
     stage_report = {k: v for k, v in stages.items()}
     stage_report["sort_pass_ms"] = pass_ms
@@ -290,6 +293,7 @@ def main():
         stage_report["view_gbs_88B"] = N_SPLATS * 88.25 / (stages["view_ms"] * 1e-3) / 1e9
     if stages.get("distances_ms"):
         stage_report["distances_gbs_12B"] = N_SPLATS * 12.25 / (stages["distances_ms"] * 1e-3) / 1e9
+    stage_report["dominant_kernel_by_time"] = "k_raster (issue-bound: sm 64%, dram <1%; see profiles/), then k_onesweep x6"
     stage_report["frame_frac_of_hbm_roofline"] = (N_SPLATS * FRAME_BYTES_PER_SPLAT + WIDTH * HEIGHT * 8) / (ms_step * 1e-3) / 1e9 / peak
 
     cpu = None
