@@ -56,6 +56,7 @@ struct GsAsset {
   gs::AssetView av{};
   void *d_pos = nullptr, *d_other = nullptr, *d_sh = nullptr, *d_color = nullptr, *d_chunks = nullptr;
   uint32_t *order = nullptr, *keys = nullptr, *key_table = nullptr, *view = nullptr, *rect = nullptr, *d_n = nullptr;
+  float4 *draw = nullptr;  // raster-ready 48-byte records of the drawable splats
   bool view_valid = false;
   uint32_t view_w = 0, view_h = 0;
 };
@@ -119,8 +120,8 @@ static FrameConsts make_frame_consts(const GsFrameParams *fp) {
   fc.shOnly = fp->sh_only;
   fc.cutoutCount = fp->cutouts ? fp->cutout_count : 0;
   fc.bitsValid = fp->deleted_bits ? 1u : 0u;
-  fc.tilesX = ((uint32_t)fp->screen_w + kTile - 1) / kTile;
-  fc.tilesY = ((uint32_t)fp->screen_h + kTile - 1) / kTile;
+  fc.binsX = ((uint32_t)fp->screen_w + kBin - 1) / kBin;
+  fc.binsY = ((uint32_t)fp->screen_h + kBin - 1) / kBin;
   return fc;
 }
 
@@ -215,8 +216,8 @@ static int upload_frame_inputs(GsContext *ctx, GsAsset *as, const GsFrameParams 
 static int check_params(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
   if (!ctx || !as || !fp) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "null context/asset/params");
   if (as->ctx != ctx) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "asset belongs to another context");
-  if (!(fp->screen_w >= 1.0f) || !(fp->screen_h >= 1.0f) || fp->screen_w > 4080.0f || fp->screen_h > 4080.0f)
-    return fail(ctx, GS_ERR_INVALID_ARGUMENT, "screen size must be in [1,4080] (8-bit tile indices)");
+  if (!(fp->screen_w >= 1.0f) || !(fp->screen_h >= 1.0f) || fp->screen_w > 8160.0f || fp->screen_h > 8160.0f)
+    return fail(ctx, GS_ERR_INVALID_ARGUMENT, "screen size must be in [1,8160] (8-bit bin indices)");
   if (fp->sh_order > 3) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "sh_order must be 0..3");
   return GS_OK;
 }
@@ -241,7 +242,7 @@ static int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const F
   int rc = upload_frame_inputs(ctx, as, fp);
   if (rc) return rc;
   rec(ctx, EV_VIEW0);
-  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, cull, ctx->stream);
+  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, as->draw, cull, ctx->stream);
   rec(ctx, EV_VIEW1);
   ctx->launches += 1;
   as->view_valid = true;
@@ -254,12 +255,12 @@ static int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const F
 // binning + raster into a device image
 static int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const GsRenderOptions &opt, void *d_rt, uint32_t pitch,
                      uint32_t fmt) {
-  const uint32_t tiles = fc.tilesX * fc.tilesY;
+  const uint32_t tiles = fc.binsX * fc.binsY;
   int rc = ensure_bin_scratch(ctx, as->av.n, tiles, 0);
   if (rc) return rc;
   launch_binning(fc, opt, as->av.n, as->order, as->rect, ctx->bin, ctx->sort, ctx->stream);
   rec(ctx, EV_BIN1);
-  launch_raster(fc, opt, as->view, ctx->bin, d_rt, pitch, fmt, nullptr, ctx->stream);
+  launch_raster(fc, opt, as->draw, ctx->bin, d_rt, pitch, fmt, ctx->stream);
   rec(ctx, EV_RASTER1);
   ctx->launches += 1 + 2 + 1;  // bin_emit, 2 sort passes, raster
   GS_CUDA_TRY(ctx, cudaGetLastError());
@@ -408,7 +409,7 @@ int gs_asset_upload(GsContext *ctx, const GsAssetDesc *d, GsAsset **out) {
       (e = up(&as->d_sh, d->sh, d->sh_bytes)) != cudaSuccess || (e = up(&as->d_color, d->color, d->color_bytes)) != cudaSuccess ||
       (chunk_count && (e = up(&as->d_chunks, d->chunks, (uint64_t)chunk_count * 64)) != cudaSuccess) ||
       (e = cudaMalloc(&as->order, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->keys, n * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&as->key_table, n * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&as->key_table, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->draw, n * 48)) != cudaSuccess ||
       (e = cudaMalloc(&as->view, n * kViewStride + 16)) != cudaSuccess || (e = cudaMalloc(&as->rect, n * 4)) != cudaSuccess ||
       (e = cudaMalloc(&as->d_n, 4)) != cudaSuccess) {
     gs_asset_destroy(as);
@@ -432,7 +433,7 @@ void gs_asset_destroy(GsAsset *as) {
   if (!as) return;
   if (as->ctx) { cudaSetDevice(as->ctx->device); cudaStreamSynchronize(as->ctx->stream); }
   cudaFree(as->d_pos); cudaFree(as->d_other); cudaFree(as->d_sh); cudaFree(as->d_color); cudaFree(as->d_chunks);
-  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n);
+  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->draw); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n);
   delete as;
 }
 
@@ -472,7 +473,7 @@ int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRend
   GsRenderOptions opt = opt_in ? *opt_in : default_opts();
   if (opt.blend_mode > GS_BLEND_FP32) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad blend mode");
   FrameConsts fc = make_frame_consts(fp);
-  const uint32_t H = opt.band_packed ? partition_own_tile_rows(opt, fc.tilesY) * kTile : (uint32_t)fp->screen_h;
+  const uint32_t H = opt.band_packed ? partition_own_bin_rows(opt, fc.binsY) * kBin : (uint32_t)fp->screen_h;
   if ((rc = image_ok(ctx, rt, W, H, &pitch))) return rc;
   for (int e = EV_BIN1; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
   rec(ctx, EV_VIEW1);
@@ -530,7 +531,7 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
   if (opt.blend_mode > GS_BLEND_FP32) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad blend mode");
   uint32_t rt_pitch = 0, rt_fmt = GS_PIX_RGBA16F;
   FrameConsts fc = make_frame_consts(fp);
-  const uint32_t H = opt.band_packed ? partition_own_tile_rows(opt, fc.tilesY) * kTile : (uint32_t)fp->screen_h;
+  const uint32_t H = opt.band_packed ? partition_own_bin_rows(opt, fc.binsY) * kBin : (uint32_t)fp->screen_h;
   if (opt.band_packed && tgt) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "band_packed output cannot be composited before the gather");
   if (rt) { if ((rc = image_ok(ctx, rt, W, H, &rt_pitch))) return rc; rt_fmt = rt->format; }
   for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;

@@ -4,7 +4,7 @@
 
 namespace gs {
 
-constexpr uint32_t kRectEmpty = 0xFFFFFFFFu;  // tile rect sentinel (tile indices are < 255)
+constexpr uint32_t kRectEmpty = 0xFFFFFFFFu;  // bin rect sentinel (bin indices are < 255)
 
 // Screen-space footprint of one splat, derived from its SplatViewData exactly the way the
 // draw stage defines it (S/RenderGaussianSplats.shader:35-77; DESIGN.md "Raster rule").
@@ -39,12 +39,12 @@ __device__ __forceinline__ bool splat_footprint(float4 clip, float a1x, float a1
   return true;
 }
 
-// Pixel rows/cols whose centres can be touched -> inclusive tile rectangle packed x0|y0<<8|x1<<16|y1<<24.
+// Pixel rows/cols whose centres can be touched -> inclusive rectangle of 32-pixel bins packed x0|y0<<8|x1<<16|y1<<24.
 __device__ __forceinline__ uint32_t footprint_tile_rect(const SplatFootprint &fp, const FrameConsts &fc) {
   float x0 = fmaxf(ceilf(fp.cx - fp.hx - 0.5f), 0.0f), x1 = fminf(floorf(fp.cx + fp.hx - 0.5f), fc.screenW - 1.0f);
   float y0 = fmaxf(ceilf(fp.cy - fp.hy - 0.5f), 0.0f), y1 = fminf(floorf(fp.cy + fp.hy - 0.5f), fc.screenH - 1.0f);
   if (!(x0 <= x1) || !(y0 <= y1)) return kRectEmpty;
-  uint32_t tx0 = (uint32_t)x0 >> 4, tx1 = (uint32_t)x1 >> 4, ty0 = (uint32_t)y0 >> 4, ty1 = (uint32_t)y1 >> 4;
+  uint32_t tx0 = (uint32_t)x0 / kBin, tx1 = (uint32_t)x1 / kBin, ty0 = (uint32_t)y0 / kBin, ty1 = (uint32_t)y1 / kBin;
   return tx0 | (ty0 << 8) | (tx1 << 16) | (ty1 << 24);
 }
 
@@ -52,7 +52,7 @@ __device__ __forceinline__ uint32_t footprint_tile_rect(const SplatFootprint &fp
 void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s);
 void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s);
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                      uint32_t *rect, bool cull_undrawable, cudaStream_t s);
+                      uint32_t *rect, float4 *draw, bool cull_undrawable, cudaStream_t s);
 
 // Radix sort (gs_sort.cu).  Scratch layout is owned by the caller (gs_api.cu).
 struct SortScratch {
@@ -82,9 +82,9 @@ struct BinScratch {
 };
 void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
                     const BinScratch &bs, const SortScratch &sc, cudaStream_t s);
-void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const uint32_t *view, const BinScratch &bs, void *rt,
-                   uint32_t rt_pitch_bytes, uint32_t rt_format, const void *unused, cudaStream_t s);
-uint32_t partition_own_tile_rows(const GsRenderOptions &opt, uint32_t tilesY);
+void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
+                   uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s);
+uint32_t partition_own_bin_rows(const GsRenderOptions &opt, uint32_t binsY);
 void launch_unshuffle(const void *gathered, uint32_t parts, uint32_t band, uint32_t rows_pp, uint32_t fmt, void *out, uint32_t pitch,
                       uint32_t W, uint32_t H, cudaStream_t s);
 void launch_composite(const void *rt, uint32_t rt_pitch, uint32_t rt_format, void *target, uint32_t tgt_pitch, uint32_t tgt_format,

@@ -4,13 +4,16 @@
 // fixed-function blending `Blend OneMinusDstAlpha One` into an RGBA16F target
 // (S/RenderGaussianSplats.shader:10-12,35-108; draw call R/GaussianSplatRenderer.cs:156-165).
 // A CUDA device has neither rasteriser nor ROP, so the same pixels are produced by:
-//   1. bin   -- walk the splats in sorted order; each emits one (tile id, splat id) entry per
-//               16x16 screen tile its visible footprint can touch (rect written by
-//               k_calc_view).  Emission order == depth order, so one STABLE 16-bit radix sort
+//   1. bin   -- walk the splats in sorted order; each emits one (bin id, splat id) entry per
+//               32x32-pixel bin its visible footprint can touch (rect written by k_calc_view).
+//               Bins are coarser than the 16x16 raster tiles on purpose: 2.5x fewer entries to
+//               emit and sort, and the per-warp ballot cull below makes a foreign entry cost 1/32
+//               of an evaluation.  Emission order == depth order, so one STABLE 16-bit radix sort
 //               by tile id (2 onesweep passes) yields per-tile lists that are already in
 //               draw order.  No 64-bit (tile|depth) re-sort of duplicated keys.
 //   2. raster-- one CTA per tile, one pixel per thread.  The tile's list is consumed in
-//               batches staged in shared memory; every warp owns an 8x4 pixel block and
+//               batches of 256 raster-ready records (written by k_calc_view) that land in shared
+//               memory by cp.async, double buffered; every warp owns an 8x4 pixel block and
 //               first culls a batch against that block with one ballot per 32 splats, so
 //               small splats cost 1/32 of a pixel evaluation where they do not land.
 //               Blending reproduces the ROP: dst = src*(1-dst.a) + dst, rounded to half after
@@ -188,18 +191,18 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
   }
 }
 
-int bin_sort_bits(uint32_t tiles) { return tiles <= 4096u ? 6 : tiles <= 16384u ? 7 : 8; }
+int bin_sort_bits(uint32_t bins) { return bins <= 1024u ? 5 : bins <= 4096u ? 6 : bins <= 16384u ? 7 : 8; }
 
 void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
                     const BinScratch &bs, const SortScratch &sc, cudaStream_t s) {
   const Partition part = make_partition(opt);
-  const uint32_t tiles = fc.tilesX * fc.tilesY;
+  const uint32_t tiles = fc.binsX * fc.binsY;
   if (!n) { cudaMemsetAsync(bs.entry_count, 0, 16, s); return; }
   const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
   cudaMemsetAsync(bs.block_sums, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
   const int bits = bin_sort_bits(tiles);
   cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
-  k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, n, part, fc.tilesX, bs.block_sums + 1, bs.block_sums, nblocks, bs.capacity,
+  k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, n, part, fc.binsX, bs.block_sums + 1, bs.block_sums, nblocks, bs.capacity,
                                      bs.tile_keys, bs.tile_vals, bs.entry_count, sc.ghist, (uint32_t)bits);
   launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, 2, bits, true, sc, s);
 }
@@ -224,22 +227,32 @@ __device__ __forceinline__ uint32_t lower_bound32(const uint32_t *__restrict__ k
   return lo + __popc(below);
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <bool FP16_ROP, int OUT_FMT>
 __global__ void __launch_bounds__(256)
-k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, const uint32_t *__restrict__ tile_keys,
+k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const uint32_t *__restrict__ tile_keys,
          const uint32_t *__restrict__ tile_vals, const uint32_t *__restrict__ entry_count, uint8_t *__restrict__ rt, uint32_t pitch,
          uint32_t band_packed) {
-  __shared__ float4 s_a[256];  // cx, cy, i1x, i1y
-  __shared__ float4 s_b[256];  // i2x, i2y, opacity, hx
-  __shared__ float4 s_c[256];  // r, g, b, hy
+  // two staging buffers of 256 raster records (3 x float4 each): batch k+1 lands by cp.async while batch k is composited
+  __shared__ float4 s_rec[2][3][256];  // [buf][0]: cx, cy, i1x, i1y   [1]: i2x, i2y, opacity, hx   [2]: r, g, b, hy
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tx = blockIdx.x, ty = part.kth_own_row(blockIdx.y);
+  // grid: x = 16-pixel tile column, y = 2 * (own 32-pixel bin row) + (upper | lower tile row of that bin row)
+  constexpr uint32_t R = kBin / kTile;   // raster tiles per bin edge
+  const uint32_t tx = blockIdx.x, brow = part.kth_own_row(blockIdx.y / R), ty = brow * R + (blockIdx.y % R);
+  if (ty * kTile >= (uint32_t)fc.screenH) return;
   // the tile's [start,end) in the tile-sorted entry list: two warp-wide 32-ary searches (5 probes for 10M entries)
   __shared__ uint2 s_range;
   if (warp == 0) {
     const uint32_t m = __ldg(entry_count);
-    const uint32_t tile = ty * fc.tilesX + tx;
+    const uint32_t tile = brow * fc.binsX + (tx / R);   // the bin this tile lies in: R*R tiles share one list
     const uint32_t a = lower_bound32(tile_keys, m, tile, lane);
     const uint32_t b = lower_bound32(tile_keys, m, tile + 1, lane);
     if (lane == 0) s_range = make_uint2(a, b);
@@ -254,37 +267,28 @@ k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, cons
 
   float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;  // ClearRenderTarget(0,0,0,0), R/GaussianSplatRenderer.cs:196
 
-  // software pipeline: the next batch's records are in flight while this one is composited
-  float2 r0, r1, r2, r3;
-  uint2 rcol;
-  bool have = false;
-  auto prefetch = [&](uint32_t e) {
-    have = e < range.y;
-    if (have) {
-      const uint32_t id = __ldg(tile_vals + e);
-      const float2 *p = reinterpret_cast<const float2 *>(view + (size_t)id * 10);  // 40-byte stride: 8-byte aligned
-      r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2); r3 = __ldg(p + 3);
-      rcol = __ldg(reinterpret_cast<const uint2 *>(p + 4));
+  // three-deep pipeline: splat ids of batch k+2 (register) -> records of batch k+1 (cp.async in flight) -> batch k (composited)
+  auto load_id = [&](uint32_t e) -> uint32_t { return e < range.y ? __ldg(tile_vals + e) : 0xFFFFFFFFu; };
+  auto stage = [&](int buf, uint32_t id) {
+    if (id != 0xFFFFFFFFu) {
+      const float4 *src = draw + (size_t)id * 3;
+      cp_async16(&s_rec[buf][0][tid], src);
+      cp_async16(&s_rec[buf][1][tid], src + 1);
+      cp_async16(&s_rec[buf][2][tid], src + 2);
     }
+    cp_async_commit();
   };
-  prefetch(range.x + tid);
+  uint32_t id_next = load_id(range.x + tid);
+  stage(0, id_next);
+  id_next = load_id(range.x + 256 + tid);
 
-  for (uint32_t base = range.x; base < range.y; base += 256) {
-    {  // stage the prefetched record as a footprint
-      SplatFootprint fp;
-      bool ok = false;
-      float cr = 0.f, cg = 0.f, cb = 0.f;
-      if (have) {
-        ok = splat_footprint(make_float4(r0.x, r0.y, r1.x, r1.y), r2.x, r2.y, r3.x, r3.y, f16lo(rcol.y), fc.screenW, fc.screenH, fp);
-        cr = f16hi(rcol.x); cg = f16lo(rcol.x); cb = f16hi(rcol.y);  // shader :48-51
-      }
-      if (!ok) { fp.cx = fp.cy = fp.i1x = fp.i1y = fp.i2x = fp.i2y = fp.ca = 0.f; fp.hx = fp.hy = -1.0e9f; }
-      s_a[tid] = make_float4(fp.cx, fp.cy, fp.i1x, fp.i1y);
-      s_b[tid] = make_float4(fp.i2x, fp.i2y, fp.ca, fp.hx);
-      s_c[tid] = make_float4(cr, cg, cb, fp.hy);
-    }
-    __syncthreads();
-    prefetch(base + 256 + tid);
+  int buf = 0;
+  for (uint32_t base = range.x; base < range.y; base += 256, buf ^= 1) {
+    stage(buf ^ 1, id_next);                       // batch k+1 -> other buffer (free since the barrier that ended batch k-1)
+    id_next = load_id(base + 512 + tid);           // ids of batch k+2
+    cp_async_wait<1>();                            // batch k has landed (this thread's copies) ...
+    __syncthreads();                               // ... and everyone else's
+    const float4 *s_a = s_rec[buf][0], *s_b = s_rec[buf][1], *s_c = s_rec[buf][2];
 
     const uint32_t cnt = min(256u, range.y - base);
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
@@ -319,12 +323,14 @@ k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, cons
         }
       }
     }
-    // a pixel whose dst.a == 1 ignores every later splat exactly (src*0 + dst): safe early out
+    // a pixel whose dst.a == 1 ignores every later splat exactly (src*0 + dst): safe early out.  The barrier also
+    // frees this batch's buffer for the copies issued at the top of the next-but-one iteration.
     if (__syncthreads_and(d3 == 1.0f || !in_image)) break;
   }
+  cp_async_wait<0>();
 
   if (in_image) {
-    const uint32_t out_row = band_packed ? blockIdx.y * kTile + (py - ty * kTile) : py;
+    const uint32_t out_row = band_packed ? (blockIdx.y / R) * kBin + (py - brow * kBin) : py;
     uint8_t *row = rt + (size_t)out_row * pitch;
     if (OUT_FMT == GS_PIX_RGBA16F) {
       uint2 o;
@@ -337,35 +343,35 @@ k_raster(FrameConsts fc, Partition part, const uint32_t *__restrict__ view, cons
   }
 }
 
-void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const uint32_t *view, const BinScratch &bs, void *rt,
-                   uint32_t rt_pitch_bytes, uint32_t rt_format, const void *, cudaStream_t s) {
+void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
+                   uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s) {
   const Partition part = make_partition(opt);
-  const uint32_t rows = part.own_rows_below(fc.tilesY);
-  if (!rows || !fc.tilesX) return;
-  dim3 grid(fc.tilesX, rows);
+  const uint32_t rows = part.own_rows_below(fc.binsY);
+  if (!rows || !fc.binsX) return;
+  dim3 grid(((uint32_t)fc.screenW + kTile - 1) / kTile, rows * (kBin / kTile));
   const bool rop = opt.blend_mode == GS_BLEND_FP16_ROP;
   uint8_t *out = reinterpret_cast<uint8_t *>(rt);
   if (rt_format == GS_PIX_RGBA16F) {
-    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
-    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
+    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, draw, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
+    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, draw, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
   } else {
-    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
-    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, view, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
+    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, draw, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
+    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, draw, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
   }
 }
 
-uint32_t partition_own_tile_rows(const GsRenderOptions &opt, uint32_t tilesY) { return make_partition(opt).own_rows_below(tilesY); }
+uint32_t partition_own_bin_rows(const GsRenderOptions &opt, uint32_t binsY) { return make_partition(opt).own_rows_below(binsY); }
 
 // ---- 2b. multi-GPU epilogue: gathered band-packed targets -> one image ---------------------------
 __global__ void __launch_bounds__(256) k_unshuffle(const uint8_t *__restrict__ gathered, Partition part, uint32_t rows_pp, uint32_t px_bytes,
                                                    uint8_t *__restrict__ out, uint32_t pitch, uint32_t W, uint32_t H) {
   const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= W || y >= H) return;
-  const uint32_t ty = y / kTile;
+  const uint32_t ty = y / kBin;
   Partition owner = part;
   owner.index = part.count > 1 ? (ty / part.band) % part.count : 0;
   const uint32_t k = owner.own_rows_below(ty);
-  const uint8_t *src = gathered + ((size_t)owner.index * rows_pp + (size_t)k * kTile + (y - ty * kTile)) * W * px_bytes;
+  const uint8_t *src = gathered + ((size_t)owner.index * rows_pp + (size_t)k * kBin + (y - ty * kBin)) * W * px_bytes;
   if (px_bytes == 8) reinterpret_cast<uint2 *>(out + (size_t)y * pitch)[x] = reinterpret_cast<const uint2 *>(src)[x];
   else reinterpret_cast<uint4 *>(out + (size_t)y * pitch)[x] = reinterpret_cast<const uint4 *>(src)[x];
 }

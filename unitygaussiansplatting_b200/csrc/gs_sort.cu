@@ -337,6 +337,7 @@ void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, 
     cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
     const uint32_t grid = min(tiles, 148u * 8u);
     if (passes == 4) k_sort_hist<4, 8><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
+    else if (bits == 5) k_sort_hist<2, 5><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
     else if (bits == 6) k_sort_hist<2, 6><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
     else if (bits == 7) k_sort_hist<2, 7><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
     else k_sort_hist<2, 8><<<grid, 256, 0, s>>>(keys, d_count, sc.ghist);
@@ -355,7 +356,8 @@ void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, 
     uint32_t *lb = sc.lookback + (size_t)p * tiles * nb;
     const bool gather = key_table != nullptr && p == 0;   // pass 0 reads key_table[vals[i]] instead of keys[i]
     const uint32_t *src_keys = gather ? key_table : sk;
-    if (bits == 6) launch_pass<6>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
+    if (bits == 5) launch_pass<5>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
+    else if (bits == 6) launch_pass<6>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
     else if (bits == 7) launch_pass<7>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
     else launch_pass<8>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
     uint32_t *t = sk; sk = dk; dk = t;

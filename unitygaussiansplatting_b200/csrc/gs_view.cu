@@ -204,7 +204,7 @@ __device__ __forceinline__ float3 neg(float3 a) { return make_float3(-a.x, -a.y,
 template <int SHFMT, bool CULL>
 __global__ void __launch_bounds__(256)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
-            uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out) {
+            uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out) {
   __shared__ __align__(16) uint32_t s_view[256 * 10];
   __shared__ __align__(16) Chunk s_chunk;
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
@@ -416,8 +416,17 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
         vw[9] = (f32tof16(res.z) << 16) | f32tof16(alpha);
       }
       SplatFootprint fp;
-      if (drawable && splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp))
+      if (drawable && splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp)) {
         rect = footprint_tile_rect(fp, fc);
+        if (rect != kRectEmpty) {
+          // raster-ready record (48 B): everything the per-pixel loop needs, so the compositor stages it with three
+          // 16-byte async copies and no arithmetic.  Colours are the half-rounded values of the SplatViewData record.
+          float4 *d = draw_out + (size_t)idx * 3;
+          d[0] = make_float4(fp.cx, fp.cy, fp.i1x, fp.i1y);
+          d[1] = make_float4(fp.i2x, fp.i2y, fp.ca, fp.hx);
+          d[2] = make_float4(f16hi(vw[8]), f16lo(vw[8]), f16hi(vw[9]), fp.hy);
+        }
+      }
     }
     rect_out[idx] = rect;
   }
@@ -453,21 +462,21 @@ void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *
 
 template <bool CULL>
 static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                               uint32_t *rect, cudaStream_t s) {
+                               uint32_t *rect, float4 *draw, cudaStream_t s) {
   const uint32_t grid = (a.n + 255) / 256;
   switch (a.shFmt) {
-    case 0: k_calc_view<0, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
-    case 1: k_calc_view<1, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
-    case 2: k_calc_view<2, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
-    default: k_calc_view<3, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect); break;
+    case 0: k_calc_view<0, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw); break;
+    case 1: k_calc_view<1, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw); break;
+    case 2: k_calc_view<2, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw); break;
+    default: k_calc_view<3, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw); break;
   }
 }
 
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                      uint32_t *rect, bool cull_undrawable, cudaStream_t s) {
+                      uint32_t *rect, float4 *draw, bool cull_undrawable, cudaStream_t s) {
   if (!a.n) return;
-  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, view, rect, s);
-  else launch_calc_view_t<false>(a, fc, cutouts, deleted, view, rect, s);
+  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, view, rect, draw, s);
+  else launch_calc_view_t<false>(a, fc, cutouts, deleted, view, rect, draw, s);
 }
 
 }  // namespace gs
