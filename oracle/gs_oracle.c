@@ -437,44 +437,62 @@ void gso_calc_view(const GsoAsset *a, const GsoFrame *f, GsoView *view, int thre
 /* ------------------------------------------------------------------ draw + blend */
 static inline float round_h(float v) { return gso_f16tof32(gso_f32tof16(v)); }
 
+typedef struct DrawRec { /* per-splat constants of the draw, computed once (phase 1) */
+  float cx, cy, i1x, i1y, i2x, i2y, cr, cg, cb, ca;
+  int32_t x0, x1, y0, y1; /* pixel rectangle to visit; x0 >= x1 marks "nothing to draw" */
+} DrawRec;
+
 void gso_render(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t W, uint32_t H, uint32_t blend_mode,
                 float *rt, int threads) {
   memset(rt, 0, (size_t)W * H * 16); /* ClearRenderTarget(0,0,0,0), R/GaussianSplatRenderer.cs:196 */
   if (threads < 1) threads = 1;
-  if ((uint32_t)threads > H) threads = (int)H;
   const float fW = (float)W, fH = (float)H;
-#pragma omp parallel num_threads(threads)
-  {
-#ifdef _OPENMP
-    int t = omp_get_thread_num(), T = omp_get_num_threads();
-#else
-    int t = 0, T = 1;
-#endif
-    /* each thread owns a band of rows and walks ALL splats in order: identical result for any T */
-    const int32_t row0 = (int32_t)((uint64_t)H * t / T), row1 = (int32_t)((uint64_t)H * (t + 1) / T);
+  DrawRec *recs = (DrawRec *)malloc((size_t)(n ? n : 1) * sizeof(DrawRec));
+  /* phase 1: the vertex-shader part, one record per splat in draw order (instID = _OrderBuffer[instID], :38-39) */
+#pragma omp parallel for schedule(static) num_threads(threads)
+  for (int64_t k = 0; k < (int64_t)n; ++k) {
+    const GsoView *v = &view[order[k]];
+    DrawRec *r = &recs[k];
+    r->x0 = 0; r->x1 = 0; r->y0 = 0; r->y1 = 0;
+    if (!(v->pos[3] > 0.0f)) continue;            /* behindCam -> NaN vertex -> primitive dropped, :41-45 */
+    float a1x = v->axis1[0], a1y = v->axis1[1], a2x = v->axis2[0], a2y = v->axis2[1];
+    float cr = gso_f16tof32(v->color[0] >> 16), cg = gso_f16tof32(v->color[0]), cb = gso_f16tof32(v->color[1] >> 16),
+          ca = gso_f16tof32(v->color[1]);          /* :48-51 */
+    if (!(ca >= 0.0f)) continue;                   /* "selected" branch needs valid edit bits: out of scope */
+    /* centre in pixels: D3D viewport transform of clip.xy / clip.w */
+    float ndx = v->pos[0] / v->pos[3], ndy = v->pos[1] / v->pos[3];
+    float cx = fmaf(ndx, 0.5f, 0.5f) * fW, cy = fmaf(ndy, -0.5f, 0.5f) * fH;
+    /* the quad spans centre +- 2*axis1 +- 2*axis2 (:54-61); one NDC unit = W/2 (H/2) pixels, y down */
+    float ex = 2.0f * (fabsf(a1x) + fabsf(a2x)), ey = 2.0f * (fabsf(a1y) + fabsf(a2y));
+    if (!(ex < 1.0e6f) || !(ey < 1.0e6f) || !(fabsf(cx) < 1.0e7f) || !(fabsf(cy) < 1.0e7f)) continue; /* NaN/inf axes: no raster */
+    float fx0 = floorf(cx - ex - 1.0f), fx1 = ceilf(cx + ex + 1.0f), fy0 = floorf(cy - ey - 1.0f), fy1 = ceilf(cy + ey + 1.0f);
+    int32_t x0 = fx0 < 0.0f ? 0 : (int32_t)fx0, x1 = fx1 > fW ? (int32_t)W : (int32_t)fx1;
+    int32_t y0 = fy0 < 0.0f ? 0 : (int32_t)fy0, y1 = fy1 > fH ? (int32_t)H : (int32_t)fy1;
+    if (x0 >= x1 || y0 >= y1) continue;
+    /* quad coordinates of a pixel: d = qa*axis1 + qb*axis2, axes orthogonal */
+    float n1 = a1x * a1x + a1y * a1y, n2 = a2x * a2x + a2y * a2y;
+    r->cx = cx; r->cy = cy;
+    r->i1x = a1x / n1; r->i1y = a1y / n1; r->i2x = a2x / n2; r->i2y = a2y / n2;
+    r->cr = cr; r->cg = cg; r->cb = cb; r->ca = ca;
+    r->x0 = x0; r->x1 = x1; r->y0 = y0; r->y1 = y1;
+  }
+  /* phase 2: rasterise + blend.  Each thread owns a band of rows and walks ALL splats in draw order, so the result
+     does not depend on the thread count. */
+  int bands = threads;
+  if ((uint32_t)bands > H) bands = (int)H;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (int t = 0; t < bands * 4; ++t) {
+    const int32_t row0 = (int32_t)((uint64_t)H * t / (bands * 4)), row1 = (int32_t)((uint64_t)H * (t + 1) / (bands * 4));
     for (uint32_t k = 0; k < n; ++k) {
-      const GsoView *v = &view[order[k]];           /* instID = _OrderBuffer[instID], shader :38-39 */
-      if (!(v->pos[3] > 0.0f)) continue;            /* behindCam -> NaN vertex -> primitive dropped, :41-45 */
-      float a1x = v->axis1[0], a1y = v->axis1[1], a2x = v->axis2[0], a2y = v->axis2[1];
-      float cr = gso_f16tof32(v->color[0] >> 16), cg = gso_f16tof32(v->color[0]), cb = gso_f16tof32(v->color[1] >> 16),
-            ca = gso_f16tof32(v->color[1]);          /* :48-51 */
-      if (!(ca >= 0.0f)) continue;                   /* "selected" branch needs valid edit bits: out of scope */
-      /* centre in pixels: D3D viewport transform of clip.xy / clip.w */
-      float ndx = v->pos[0] / v->pos[3], ndy = v->pos[1] / v->pos[3];
-      float cx = fmaf(ndx, 0.5f, 0.5f) * fW, cy = fmaf(ndy, -0.5f, 0.5f) * fH;
-      /* the quad spans centre +- 2*axis1 +- 2*axis2 (:54-61); one NDC unit = W/2 (H/2) pixels, y down */
-      float ex = 2.0f * (fabsf(a1x) + fabsf(a2x)), ey = 2.0f * (fabsf(a1y) + fabsf(a2y));
-      if (!(ex < 1.0e6f) || !(ey < 1.0e6f) || !(fabsf(cx) < 1.0e7f) || !(fabsf(cy) < 1.0e7f)) continue; /* NaN/inf axes: no raster */
-      float fx0 = floorf(cx - ex - 1.0f), fx1 = ceilf(cx + ex + 1.0f), fy0 = floorf(cy - ey - 1.0f), fy1 = ceilf(cy + ey + 1.0f);
-      int32_t x0 = fx0 < 0.0f ? 0 : (int32_t)fx0, x1 = fx1 > fW ? (int32_t)W : (int32_t)fx1;
-      int32_t y0 = fy0 < (float)row0 ? row0 : (int32_t)fy0, y1 = fy1 > (float)row1 ? row1 : (int32_t)fy1;
-      if (x0 >= x1 || y0 >= y1) continue;
-      /* quad coordinates of a pixel: d = qa*axis1 + qb*axis2, axes orthogonal */
-      float n1 = a1x * a1x + a1y * a1y, n2 = a2x * a2x + a2y * a2y;
-      float i1x = a1x / n1, i1y = a1y / n1, i2x = a2x / n2, i2y = a2y / n2;
+      const DrawRec *r = &recs[k];
+      if (r->x0 >= r->x1) continue;
+      const int32_t y0 = r->y0 < row0 ? row0 : r->y0, y1 = r->y1 > row1 ? row1 : r->y1;
+      if (y0 >= y1) continue;
+      const float cx = r->cx, cy = r->cy, i1x = r->i1x, i1y = r->i1y, i2x = r->i2x, i2y = r->i2y;
+      const float cr = r->cr, cg = r->cg, cb = r->cb, ca = r->ca;
       for (int32_t py = y0; py < y1; ++py) {
         float dy = cy - ((float)py + 0.5f); /* pixel y grows downwards, NDC y upwards */
-        for (int32_t px = x0; px < x1; ++px) {
+        for (int32_t px = r->x0; px < r->x1; ++px) {
           float dx = ((float)px + 0.5f) - cx;
           float qa = fmaf(dy, i1y, dx * i1x), qb = fmaf(dy, i2y, dx * i2x);
           if (!(fabsf(qa) <= 2.0f && fabsf(qb) <= 2.0f)) continue; /* outside the quad */
@@ -491,6 +509,7 @@ void gso_render(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t
       }
     }
   }
+  free(recs);
 }
 
 /* ------------------------------------------------------------------ composite */
