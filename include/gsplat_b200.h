@@ -183,8 +183,9 @@ GS_API int gs_composite(GsContext *ctx, const GsImage *rt, GsImage *camera_targe
  * R/GaussianSplatRenderer.cs:120-121.  rt may be NULL when camera_target is given
  * (the RT then lives only in library scratch).
  * The fused path treats the colour of a splat that cannot produce a fragment (quad off screen, or
- * opacity below the 1/255 discard) as dead code: its _SplatViewData record keeps pos/axes exactly and
- * gets colour = 0.  Pixels are unaffected; call gs_calc_view for the complete buffer. */
+ * opacity below the 1/255 discard) as dead code: its _SplatViewData record keeps pos exactly, gets
+ * colour = 0 and, when a cheap extent bound already puts it off screen, axes = 0.  Pixels are
+ * unaffected; call gs_calc_view for the complete buffer. */
 GS_API int gs_frame(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp,
                     const GsRenderOptions *opt, int do_sort, GsImage *rt, GsImage *camera_target);
 
@@ -207,6 +208,10 @@ GS_API int gs_readback_order(GsAsset *asset, uint32_t *dst);      /* _SplatSortK
 GS_API int gs_readback_keys(GsAsset *asset, uint32_t *dst);       /* _SplatSortDistances, N words (sorted after gs_sort) */
 GS_API int gs_readback_view(GsAsset *asset, void *dst);           /* _SplatViewData, N x 40 bytes (S/GaussianSplatting.hlsl:610-615) */
 GS_API int gs_upload_order(GsAsset *asset, const uint32_t *src);  /* seed a previous-frame order */
+
+/* Diagnostics: with GS_RASTER_STATS=1 in the environment the compositor counts, per frame, [0] warp-batches,
+ * [1] warp cull ballots, [2] warp candidates, [3] warp evaluations, [4] pixel blends, [5] list entries x warps. */
+GS_API int gs_debug_raster_stats(GsContext *ctx, uint64_t out[8]);
 
 /* ---- device-pointer access for zero-copy hosts (torch / CUDA-Vulkan interop) ----- */
 GS_API void *gs_context_stream(GsContext *ctx);

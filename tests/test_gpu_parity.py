@@ -26,10 +26,13 @@ def _frame_pair(g, O, ctx, asset, cam, blend=0, prev_order=None, **knobs):
     fused_view = r.readback_view()
     r.CalcViewData(cam)      # the stand-alone entry point writes every record in full (gs_frame skips colour of undrawable splats)
     got = {"keys": r.readback_keys(), "order": r.readback_order(), "view": r.readback_view(), "rt": rt.astype(np.float32)}
-    # fused-frame records: pos/axes always exact; colour exact, or zero for a splat that cannot produce a fragment
-    assert np.array_equal(fused_view[:, :8], ref["view"][:, :8])
+    # fused-frame records: pos always exact; a splat that cannot produce a fragment may have colour = 0 and (when even a
+    # cheap extent bound puts it off screen) axes = 0; everything else is exact
+    assert np.array_equal(fused_view[:, :4], ref["view"][:, :4])
     czero = (fused_view[:, 8:] == 0).all(axis=1)
-    assert np.array_equal(fused_view[~czero, 8:], ref["view"][~czero, 8:])
+    azero = (fused_view[:, 4:8] == 0).all(axis=1) & czero
+    assert np.array_equal(fused_view[~czero], ref["view"][~czero])
+    assert np.array_equal(fused_view[~azero, 4:8], ref["view"][~azero, 4:8])
     r.Dispose()
     return got, ref
 

@@ -100,6 +100,7 @@ NATIVE_SYMBOLS = {
     "gs_readback_keys": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gs_readback_view": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gs_upload_order": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gs_debug_raster_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gs_context_stream": (C.c_void_p, [C.c_void_p]),
     "gs_asset_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
 }

@@ -114,6 +114,12 @@ static FrameConsts make_frame_consts(const GsFrameParams *fp) {
   fc.focal = fp->screen_w * p00 / 2.0f;
   fc.splatScale2 = fp->splat_scale * fp->splat_scale;
   fc.opacityScale = fp->opacity_scale;
+  {
+    float w2 = 0.0f;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) w2 += M_(mv, r, c) * M_(mv, r, c);
+    fc.extentK = fc.focal * fc.focal * (2.0f + fc.limX * fc.limX + fc.limY * fc.limY) * w2 * fc.splatScale2;
+  }
   fc.screenW = fp->screen_w;
   fc.screenH = fp->screen_h;
   fc.shOrder = fp->sh_order;
@@ -172,7 +178,13 @@ static int ensure_bin_scratch(GsContext *ctx, uint32_t n, uint32_t tiles, uint32
     GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.block_sums, (size_t)blocks * 4));
     ctx->bin_blocks_cap = blocks;
   }
-  (void)tiles;
+  if (tiles > ctx->tiles_cap) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->bin.bin_ranges);
+    ctx->bin.bin_ranges = nullptr;
+    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.bin_ranges, (size_t)tiles * 8));
+    ctx->tiles_cap = tiles;
+  }
   return GS_OK;
 }
 
@@ -262,7 +274,7 @@ static int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const G
   rec(ctx, EV_BIN1);
   launch_raster(fc, opt, as->draw, ctx->bin, d_rt, pitch, fmt, ctx->stream);
   rec(ctx, EV_RASTER1);
-  ctx->launches += 1 + 2 + 1;  // bin_emit, 2 sort passes, raster
+  ctx->launches += 1 + 2 + 2;  // bin_emit, 2 sort passes, bin_ranges, raster
   GS_CUDA_TRY(ctx, cudaGetLastError());
   return GS_OK;
 }
@@ -334,7 +346,7 @@ void gs_destroy(GsContext *ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->sort.alt_keys); cudaFree(ctx->sort.alt_vals); cudaFree(ctx->sort.lookback);
   cudaFree(ctx->sort.ghist); cudaFree(ctx->sort.tickets); cudaFree(ctx->d_scalar);
-  cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
+  cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
   cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted);
   for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -639,6 +651,15 @@ int gs_upload_order(GsAsset *as, const uint32_t *src) {
   if (!as || !src) return fail(as ? as->ctx : nullptr, GS_ERR_INVALID_ARGUMENT, "null argument");
   GS_CUDA_TRY(as->ctx, cudaMemcpyAsync(as->order, src, (size_t)as->av.n * 4, cudaMemcpyHostToDevice, as->ctx->stream));
   GS_CUDA_TRY(as->ctx, cudaStreamSynchronize(as->ctx->stream));
+  return GS_OK;
+}
+
+int gs_debug_raster_stats(GsContext *ctx, uint64_t out[8]) {
+  if (!ctx || !out) return GS_ERR_INVALID_ARGUMENT;
+  memset(out, 0, 64);
+  if (!g_raster_stats) return GS_ERR_NOT_READY;
+  GS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  GS_CUDA_TRY(ctx, cudaMemcpy(out, g_raster_stats, 64, cudaMemcpyDeviceToHost));
   return GS_OK;
 }
 

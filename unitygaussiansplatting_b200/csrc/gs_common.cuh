@@ -45,6 +45,7 @@ struct FrameConsts {
   float sort_row[4]; // row 2 of (diag(1,1,-1)*view) * o2w  -- CSCalcDistances
   float cam_pos[3];
   float limX, limY, focal, splatScale2, opacityScale;
+  float extentK;     // focal^2 * (2 + limX^2 + limY^2) * |MV3x3|_F^2 * splatScale^2: trace(cov2d) <= extentK * smax^2 / tz^2 + 0.6
   float screenW, screenH;
   uint32_t shOrder, shOnly;
   uint32_t cutoutCount, bitsValid;

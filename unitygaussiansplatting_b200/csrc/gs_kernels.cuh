@@ -78,12 +78,14 @@ struct BinScratch {
   uint32_t *block_sums;    // [0] block ticket, [1..] look-back status of the fused count+scan+emit kernel
   uint32_t *entry_count;   // [0] = (tile,splat) entries clamped to capacity, [1] = overflow flag, [2] = unclamped total
   uint32_t *tile_keys, *tile_vals;  // capacity entries each
+  uint32_t *bin_ranges;    // uint2 [start,end) per bin
   uint32_t capacity;
 };
 void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
                     const BinScratch &bs, const SortScratch &sc, cudaStream_t s);
 void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
                    uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s);
+extern unsigned long long *g_raster_stats;   // diagnostics, see GS_RASTER_STATS
 uint32_t partition_own_bin_rows(const GsRenderOptions &opt, uint32_t binsY);
 void launch_unshuffle(const void *gathered, uint32_t parts, uint32_t band, uint32_t rows_pp, uint32_t fmt, void *out, uint32_t pitch,
                       uint32_t W, uint32_t H, cudaStream_t s);

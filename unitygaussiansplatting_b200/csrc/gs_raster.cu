@@ -19,6 +19,8 @@
 //               Blending reproduces the ROP: dst = src*(1-dst.a) + dst, rounded to half after
 //               every splat (GS_BLEND_FP16_ROP) -- or kept in float32 (GS_BLEND_FP32).
 //   3. composite (S/GaussianComposite.shader:35-39).
+#include <cstdlib>
+
 #include "gs_kernels.cuh"
 
 namespace gs {
@@ -235,11 +237,24 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// one warp per bin: [start,end) of the bin's entries in the sorted list, by two 32-ary searches (5 probes for 10M entries)
+__global__ void __launch_bounds__(256) k_bin_ranges(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ entry_count,
+                                                    uint32_t bins, uint2 *__restrict__ ranges) {
+  const uint32_t bin = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (bin >= bins) return;
+  const uint32_t m = __ldg(entry_count);
+  const uint32_t a = lower_bound32(keys, m, bin, lane), b = lower_bound32(keys, m, bin + 1, lane);
+  if (lane == 0) ranges[bin] = make_uint2(a, b);
+}
+
 template <bool FP16_ROP, int OUT_FMT>
 __global__ void __launch_bounds__(256)
-k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const uint32_t *__restrict__ tile_keys,
-         const uint32_t *__restrict__ tile_vals, const uint32_t *__restrict__ entry_count, uint8_t *__restrict__ rt, uint32_t pitch,
-         uint32_t band_packed) {
+k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const uint2 *__restrict__ bin_ranges,
+         const uint32_t *__restrict__ tile_vals, uint8_t *__restrict__ rt, uint32_t pitch,
+         uint32_t band_packed, unsigned long long *stats) {
+  uint32_t st_batches = 0, st_culls = 0, st_cand = 0, st_eval = 0, st_blend = 0;   // GS_RASTER_STATS diagnostics (per warp)
+  unsigned long long st_t0 = 0;
+  if (stats) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(st_t0));
   // two staging buffers of 256 raster records (3 x float4 each): batch k+1 lands by cp.async while batch k is composited
   __shared__ float4 s_rec[2][3][256];  // [buf][0]: cx, cy, i1x, i1y   [1]: i2x, i2y, opacity, hx   [2]: r, g, b, hy
 
@@ -248,17 +263,8 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   constexpr uint32_t R = kBin / kTile;   // raster tiles per bin edge
   const uint32_t tx = blockIdx.x, brow = part.kth_own_row(blockIdx.y / R), ty = brow * R + (blockIdx.y % R);
   if (ty * kTile >= (uint32_t)fc.screenH) return;
-  // the tile's [start,end) in the tile-sorted entry list: two warp-wide 32-ary searches (5 probes for 10M entries)
-  __shared__ uint2 s_range;
-  if (warp == 0) {
-    const uint32_t m = __ldg(entry_count);
-    const uint32_t tile = brow * fc.binsX + (tx / R);   // the bin this tile lies in: R*R tiles share one list
-    const uint32_t a = lower_bound32(tile_keys, m, tile, lane);
-    const uint32_t b = lower_bound32(tile_keys, m, tile + 1, lane);
-    if (lane == 0) s_range = make_uint2(a, b);
-  }
-  __syncthreads();
-  const uint2 range = s_range;
+  // [start,end) of this tile's bin in the bin-sorted entry list (k_bin_ranges); R*R tiles share one list
+  const uint2 range = __ldg(bin_ranges + brow * fc.binsX + (tx / R));
   const uint32_t bx = tx * kTile + (warp & 1) * 8, by = ty * kTile + (warp >> 1) * 4;
   const uint32_t px = bx + (lane & 7), py = by + (lane >> 3);
   const float pxc = (float)px + 0.5f, pyc = (float)py + 0.5f;
@@ -291,9 +297,11 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
     const float4 *s_a = s_rec[buf][0], *s_b = s_rec[buf][1], *s_c = s_rec[buf][2];
 
     const uint32_t cnt = min(256u, range.y - base);
+    ++st_batches;
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
       // a warp whose 32 pixels all reached dst.a == 1 ignores everything behind exactly: skip the batch remainder
       if (__all_sync(0xffffffffu, d3 == 1.0f || !in_image)) break;
+      ++st_culls;
       // one ballot culls 32 splats against this warp's 8x4 pixel block
       const uint32_t e = c0 + lane;
       bool hit = false;
@@ -306,19 +314,25 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
       while (mask) {
         const uint32_t j = c0 + __ffs(mask) - 1;
         mask &= mask - 1;
+        ++st_cand;
         const float4 A = s_a[j], B = s_b[j];
         const float dx = pxc - A.x, dy = A.y - pyc;  // pixel y grows down, NDC y up
         const float qa = fmaf(dy, A.w, dx * A.z), qb = fmaf(dy, B.y, dx * B.x);
         const bool inside = (fabsf(qa) <= 2.0f) && (fabsf(qb) <= 2.0f);  // quad corners at +-2 (:54-55)
         if (!__any_sync(0xffffffffu, inside)) continue;
+        ++st_eval;
         const float power = -fmaf(qb, qb, qa * qa);                       // -dot(i.pos, i.pos) (:81)
-        const float alpha = satf(exp_neg(power) * B.z);                   // :82-86
+        const float alpha = __saturatef(exp_neg(power) * B.z);            // :82-86 (saturate: NaN -> 0, one instruction)
         if (inside && alpha >= 0.003921569f) {                            // discard below 1/255 (:103-104)
+          ++st_blend;
           const float4 C = s_c[j];
           const float om = 1.0f - d3;                                     // Blend OneMinusDstAlpha One (:11)
           float n0 = fmaf(C.x * alpha, om, d0), n1 = fmaf(C.y * alpha, om, d1), n2 = fmaf(C.z * alpha, om, d2),
                 n3 = fmaf(alpha, om, d3);
-          if (FP16_ROP) { n0 = round_half(n0); n1 = round_half(n1); n2 = round_half(n2); n3 = round_half(n3); }
+          if (FP16_ROP) {  // the ROP stores half: round every channel (two packed f32x2 -> f16x2 conversions)
+            const float2 lo = __half22float2(__floats2half2_rn(n0, n1)), hi = __half22float2(__floats2half2_rn(n2, n3));
+            n0 = lo.x; n1 = lo.y; n2 = hi.x; n3 = hi.y;
+          }
           d0 = n0; d1 = n1; d2 = n2; d3 = n3;
         }
       }
@@ -328,6 +342,18 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
     if (__syncthreads_and(d3 == 1.0f || !in_image)) break;
   }
   cp_async_wait<0>();
+  if (stats) {
+    const uint32_t bl = __reduce_add_sync(0xffffffffu, st_blend);
+    if (lane == 0) {
+      atomicAdd(stats + 0, (unsigned long long)st_batches); atomicAdd(stats + 1, (unsigned long long)st_culls);
+      atomicAdd(stats + 2, (unsigned long long)st_cand); atomicAdd(stats + 3, (unsigned long long)st_eval);
+      atomicAdd(stats + 4, (unsigned long long)bl); atomicAdd(stats + 5, (unsigned long long)(range.y - range.x));
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      atomicAdd(stats + 6, t1 - st_t0);
+      atomicMax(stats + 7, t1 - st_t0);
+    }
+  }
 
   if (in_image) {
     const uint32_t out_row = band_packed ? (blockIdx.y / R) * kBin + (py - brow * kBin) : py;
@@ -343,6 +369,8 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   }
 }
 
+unsigned long long *g_raster_stats = nullptr;
+
 void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
                    uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s) {
   const Partition part = make_partition(opt);
@@ -351,12 +379,21 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const floa
   dim3 grid(((uint32_t)fc.screenW + kTile - 1) / kTile, rows * (kBin / kTile));
   const bool rop = opt.blend_mode == GS_BLEND_FP16_ROP;
   uint8_t *out = reinterpret_cast<uint8_t *>(rt);
+  // GS_RASTER_STATS=1: per-frame work counters (diagnostics; printed by tools/raster_stats.py through gs_debug_raster_stats)
+  static unsigned long long *stats = nullptr;
+  static int want = -1;
+  if (want < 0) { const char *e = getenv("GS_RASTER_STATS"); want = (e && e[0] == '1') ? 1 : 0; }
+  if (want && !stats) { cudaMalloc(&stats, 64); g_raster_stats = stats; }
+  if (stats) cudaMemsetAsync(stats, 0, 64, s);
+  const uint32_t bins = fc.binsX * fc.binsY;
+  uint2 *ranges = reinterpret_cast<uint2 *>(bs.bin_ranges);
+  k_bin_ranges<<<(bins + 7) / 8, 256, 0, s>>>(bs.tile_keys, bs.entry_count, bins, ranges);
   if (rt_format == GS_PIX_RGBA16F) {
-    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, draw, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
-    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, draw, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
+    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, out, rt_pitch_bytes, opt.band_packed, stats);
+    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, out, rt_pitch_bytes, opt.band_packed, stats);
   } else {
-    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, draw, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
-    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, draw, bs.tile_keys, bs.tile_vals, bs.entry_count, out, rt_pitch_bytes, opt.band_packed);
+    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, out, rt_pitch_bytes, opt.band_packed, stats);
+    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, out, rt_pitch_bytes, opt.band_packed, stats);
   }
 }
 

@@ -199,7 +199,8 @@ __device__ __forceinline__ float3 neg(float3 a) { return make_float3(-a.x, -a.y,
 
 // CULL (used by the fused gs_frame): a splat whose quad cannot touch the screen, or whose opacity can never reach the
 // 1/255 discard threshold, is never drawn, so its colour half of the record (SH fetch + ShadeSH, 2/3 of the bytes and
-// ~half of the arithmetic) is dead code; the record then carries pos/axes exactly and colour = 0.  gs_calc_view (the
+// ~half of the arithmetic) is dead code: the record then carries pos (and, unless even a cheap extent bound puts the
+// splat off screen, the axes) exactly, and colour = 0.  gs_calc_view (the
 // stand-alone entry point) always runs the full kernel, so _SplatViewData parity is checked on that one.
 template <int SHFMT, bool CULL>
 __global__ void __launch_bounds__(256)
@@ -323,7 +324,22 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
     if (fc.cutoutCount && is_splat_cut(fc, cutouts, pos)) clip.w = 0.0f;
     vw[0] = __float_as_uint(clip.x); vw[1] = __float_as_uint(clip.y); vw[2] = __float_as_uint(clip.z); vw[3] = __float_as_uint(clip.w);
 
-    if (!(clip.w <= 0.0f)) {
+    bool far_off = false;
+    if (CULL && clip.w > 0.0f) {
+      // Cheap conservative screen-extent bound BEFORE the covariance maths: lambda1 <= trace(cov2d) <= |J|_F^2 |W|_F^2 smax^2 + 0.6
+      // with |J|_F^2 <= focal^2 (2 + limX^2 + limY^2) / tz^2, and the +-2 quad reaches at most 4 * min(sqrt(2 lambda1), 4096)
+      // pixels from its centre.  A splat whose centre is further than that outside the screen can never produce a fragment:
+      // the fused frame stores {pos, 0, 0} for it and skips rotation, covariance, eigen-decomposition and colour.
+      const float tzq = fmaf(fc.mv[10], pos.z, fmaf(fc.mv[9], pos.y, fmaf(fc.mv[8], pos.x, fc.mv[11])));
+      const float smax = fmaxf(scale.x, fmaxf(scale.y, scale.z));
+      const float tr = fc.extentK * smax * smax / (tzq * tzq) + 0.6f;
+      const float reach = 4.04f * fminf(sqrtf(2.0f * tr), 4096.0f) + 2.0f;
+      const float iw = 1.0f / clip.w;
+      const float pcx = (clip.x * iw * 0.5f + 0.5f) * fc.screenW, pcy = (0.5f - 0.5f * clip.y * iw) * fc.screenH;
+      far_off = (pcx + reach < 0.0f) || (pcx - reach > fc.screenW) || (pcy + reach < 0.0f) || (pcy - reach > fc.screenH);
+    }
+
+    if (!(clip.w <= 0.0f) && !far_off) {
       // CalcMatrixFromRotationScale, S/GaussianSplatting.hlsl:29-46
       const float x = rot.x, y = rot.y, z = rot.z, w = rot.w;
       float m[3][3];
