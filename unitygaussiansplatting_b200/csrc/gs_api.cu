@@ -37,7 +37,7 @@ struct GsContext {
   uint32_t *d_scalar = nullptr;  // small device scalars (standalone sorter count)
   // bin scratch
   gs::BinScratch bin{};
-  uint32_t bin_blocks_cap = 0, tiles_cap = 0;
+  uint32_t bin_blocks_cap = 0, tiles_cap = 0, raster_tiles_cap = 0, raster_tiles_cur = 0;
   // image scratch
   void *rt_scratch = nullptr;
   size_t rt_bytes = 0;
@@ -270,11 +270,27 @@ static int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const G
   const uint32_t tiles = fc.binsX * fc.binsY;
   int rc = ensure_bin_scratch(ctx, as->av.n, tiles, 0);
   if (rc) return rc;
+  {  // raster-tile cost history (launch order); invalidated when the tile grid changes
+    const uint32_t rtiles = (((uint32_t)fc.screenW + kTile - 1) / kTile) * partition_own_bin_rows(opt, fc.binsY) * (kBin / kTile);
+    if (rtiles > ctx->raster_tiles_cap) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order);
+      ctx->bin.tile_cost = ctx->bin.tile_order = nullptr;
+      GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.tile_cost, (size_t)rtiles * 4));
+      GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.tile_order, (size_t)rtiles * 4));
+      ctx->raster_tiles_cap = rtiles;
+      ctx->raster_tiles_cur = 0;
+    }
+    if (rtiles != ctx->raster_tiles_cur) {
+      GS_CUDA_TRY(ctx, cudaMemsetAsync(ctx->bin.tile_cost, 0, (size_t)rtiles * 4, ctx->stream));
+      ctx->raster_tiles_cur = rtiles;
+    }
+  }
   launch_binning(fc, opt, as->av.n, as->order, as->rect, ctx->bin, ctx->sort, ctx->stream);
   rec(ctx, EV_BIN1);
   launch_raster(fc, opt, as->draw, ctx->bin, d_rt, pitch, fmt, ctx->stream);
   rec(ctx, EV_RASTER1);
-  ctx->launches += 1 + 2 + 2;  // bin_emit, 2 sort passes, bin_ranges, raster
+  ctx->launches += 1 + 2 + 3;  // bin_emit, 2 sort passes, bin_ranges, tile_order, raster
   GS_CUDA_TRY(ctx, cudaGetLastError());
   return GS_OK;
 }
@@ -346,7 +362,7 @@ void gs_destroy(GsContext *ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->sort.alt_keys); cudaFree(ctx->sort.alt_vals); cudaFree(ctx->sort.lookback);
   cudaFree(ctx->sort.ghist); cudaFree(ctx->sort.tickets); cudaFree(ctx->d_scalar);
-  cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
+  cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
   cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted);
   for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -79,6 +79,7 @@ struct BinScratch {
   uint32_t *entry_count;   // [0] = (tile,splat) entries clamped to capacity, [1] = overflow flag, [2] = unclamped total
   uint32_t *tile_keys, *tile_vals;  // capacity entries each
   uint32_t *bin_ranges;    // uint2 [start,end) per bin
+  uint32_t *tile_cost, *tile_order;   // per raster tile: last frame's cost, this frame's launch order
   uint32_t capacity;
 };
 void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,

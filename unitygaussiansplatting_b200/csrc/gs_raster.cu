@@ -247,22 +247,60 @@ __global__ void __launch_bounds__(256) k_bin_ranges(const uint32_t *__restrict__
   if (lane == 0) ranges[bin] = make_uint2(a, b);
 }
 
-template <bool FP16_ROP, int OUT_FMT>
+// Launch order of the raster tiles: longest-processing-time first, from the cost each tile measured last frame
+// (counting sort over 64 log-scale buckets, one CTA).  Pixels do not depend on the order; only the tail does.
+__global__ void __launch_bounds__(1024) k_tile_order(const uint32_t *__restrict__ cost, uint32_t ntiles, uint32_t *__restrict__ order) {
+  __shared__ uint32_t s_hist[64], s_base[64];
+  __shared__ uint32_t s_any;
+  if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  auto bucket = [](uint32_t c) -> uint32_t {   // 0 for cost 0, else 2*log2 resolution, descending order wanted
+    if (c == 0) return 0u;
+    const uint32_t l = 31u - (uint32_t)__clz(c);
+    const uint32_t half = l ? ((c >> (l - 1)) & 1u) : 0u;
+    return min(63u, 1u + 2u * l + half);
+  };
+  for (uint32_t t = threadIdx.x; t < ntiles; t += 1024) {
+    const uint32_t c = cost[t];
+    if (c) s_any = 1;
+    atomicAdd(&s_hist[63u - bucket(c)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int b = 0; b < 64; ++b) { s_base[b] = run; run += s_hist[b]; }
+  }
+  __syncthreads();
+  if (!s_any) {   // no history (first frame / new resolution): a stride permutation spreads spatial clusters
+    for (uint32_t t = threadIdx.x; t < ntiles; t += 1024) order[t] = (ntiles % 1031u) ? (uint32_t)(((uint64_t)t * 1031u) % ntiles) : t;
+    return;
+  }
+  for (uint32_t t = threadIdx.x; t < ntiles; t += 1024) order[atomicAdd(&s_base[63u - bucket(cost[t])], 1u)] = t;
+}
+
+template <bool FP16_ROP, int OUT_FMT, bool STATS>
 __global__ void __launch_bounds__(256)
 k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const uint2 *__restrict__ bin_ranges,
-         const uint32_t *__restrict__ tile_vals, uint8_t *__restrict__ rt, uint32_t pitch,
-         uint32_t band_packed, unsigned long long *stats) {
+         const uint32_t *__restrict__ tile_vals, const uint32_t *__restrict__ tile_order, uint32_t *__restrict__ tile_cost, uint32_t ntx,
+         uint8_t *__restrict__ rt, uint32_t pitch, uint32_t band_packed, unsigned long long *stats) {
   uint32_t st_batches = 0, st_culls = 0, st_cand = 0, st_eval = 0, st_blend = 0;   // GS_RASTER_STATS diagnostics (per warp)
   unsigned long long st_t0 = 0;
-  if (stats) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(st_t0));
+  if (STATS) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(st_t0));
   // two staging buffers of 256 raster records (3 x float4 each): batch k+1 lands by cp.async while batch k is composited
   __shared__ float4 s_rec[2][3][256];  // [buf][0]: cx, cy, i1x, i1y   [1]: i2x, i2y, opacity, hx   [2]: r, g, b, hy
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // grid: x = 16-pixel tile column, y = 2 * (own 32-pixel bin row) + (upper | lower tile row of that bin row)
   constexpr uint32_t R = kBin / kTile;   // raster tiles per bin edge
-  const uint32_t tx = blockIdx.x, brow = part.kth_own_row(blockIdx.y / R), ty = brow * R + (blockIdx.y % R);
-  if (ty * kTile >= (uint32_t)fc.screenH) return;
+  // launch order != raster order: CTA i takes tile order[i] (k_tile_order: most expensive first, by last frame's cost),
+  // so the expensive tiles start early instead of forming the tail
+  const uint32_t lin = __ldg(tile_order + blockIdx.x);
+  const uint32_t gy = lin / ntx;
+  const uint32_t tx = lin - gy * ntx, brow = part.kth_own_row(gy / R), ty = brow * R + (gy % R);
+  if (ty * kTile >= (uint32_t)fc.screenH) { if (threadIdx.x == 0) tile_cost[lin] = 0; return; }
+  __shared__ uint32_t s_cost;
+  if (threadIdx.x == 0) s_cost = 0;
   // [start,end) of this tile's bin in the bin-sorted entry list (k_bin_ranges); R*R tiles share one list
   const uint2 range = __ldg(bin_ranges + brow * fc.binsX + (tx / R));
   const uint32_t bx = tx * kTile + (warp & 1) * 8, by = ty * kTile + (warp >> 1) * 4;
@@ -301,7 +339,7 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
       // a warp whose 32 pixels all reached dst.a == 1 ignores everything behind exactly: skip the batch remainder
       if (__all_sync(0xffffffffu, d3 == 1.0f || !in_image)) break;
-      ++st_culls;
+      if (STATS) ++st_culls;
       // one ballot culls 32 splats against this warp's 8x4 pixel block
       const uint32_t e = c0 + lane;
       bool hit = false;
@@ -314,7 +352,7 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
       while (mask) {
         const uint32_t j = c0 + __ffs(mask) - 1;
         mask &= mask - 1;
-        ++st_cand;
+        if (STATS) ++st_cand;
         const float4 A = s_a[j], B = s_b[j];
         const float dx = pxc - A.x, dy = A.y - pyc;  // pixel y grows down, NDC y up
         const float qa = fmaf(dy, A.w, dx * A.z), qb = fmaf(dy, B.y, dx * B.x);
@@ -324,7 +362,7 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
         const float power = -fmaf(qb, qb, qa * qa);                       // -dot(i.pos, i.pos) (:81)
         const float alpha = __saturatef(exp_neg(power) * B.z);            // :82-86 (saturate: NaN -> 0, one instruction)
         if (inside && alpha >= 0.003921569f) {                            // discard below 1/255 (:103-104)
-          ++st_blend;
+          if (STATS) ++st_blend;
           const float4 C = s_c[j];
           const float om = 1.0f - d3;                                     // Blend OneMinusDstAlpha One (:11)
           float n0 = fmaf(C.x * alpha, om, d0), n1 = fmaf(C.y * alpha, om, d1), n2 = fmaf(C.z * alpha, om, d2),
@@ -342,7 +380,11 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
     if (__syncthreads_and(d3 == 1.0f || !in_image)) break;
   }
   cp_async_wait<0>();
-  if (stats) {
+  // this tile's cost for next frame's launch order: the slowest warp's work (evaluations dominate, culls and batches add)
+  if (lane == 0) atomicMax(&s_cost, st_eval * 4 + st_batches * 16 + 1);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_cost[lin] = s_cost;
+  if (STATS) {
     const uint32_t bl = __reduce_add_sync(0xffffffffu, st_blend);
     if (lane == 0) {
       atomicAdd(stats + 0, (unsigned long long)st_batches); atomicAdd(stats + 1, (unsigned long long)st_culls);
@@ -356,7 +398,7 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   }
 
   if (in_image) {
-    const uint32_t out_row = band_packed ? (blockIdx.y / R) * kBin + (py - brow * kBin) : py;
+    const uint32_t out_row = band_packed ? (gy / R) * kBin + (py - brow * kBin) : py;
     uint8_t *row = rt + (size_t)out_row * pitch;
     if (OUT_FMT == GS_PIX_RGBA16F) {
       uint2 o;
@@ -376,7 +418,9 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const floa
   const Partition part = make_partition(opt);
   const uint32_t rows = part.own_rows_below(fc.binsY);
   if (!rows || !fc.binsX) return;
-  dim3 grid(((uint32_t)fc.screenW + kTile - 1) / kTile, rows * (kBin / kTile));
+  const uint32_t ntx = ((uint32_t)fc.screenW + kTile - 1) / kTile, ntiles = ntx * rows * (kBin / kTile);
+  const uint32_t grid = ntiles;
+  k_tile_order<<<1, 1024, 0, s>>>(bs.tile_cost, ntiles, bs.tile_order);
   const bool rop = opt.blend_mode == GS_BLEND_FP16_ROP;
   uint8_t *out = reinterpret_cast<uint8_t *>(rt);
   // GS_RASTER_STATS=1: per-frame work counters (diagnostics; printed by tools/raster_stats.py through gs_debug_raster_stats)
@@ -388,13 +432,17 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const floa
   const uint32_t bins = fc.binsX * fc.binsY;
   uint2 *ranges = reinterpret_cast<uint2 *>(bs.bin_ranges);
   k_bin_ranges<<<(bins + 7) / 8, 256, 0, s>>>(bs.tile_keys, bs.entry_count, bins, ranges);
+#define GS_LAUNCH_RASTER(ROP, FMT)                                                                                              \
+  do {                                                                                                                         \
+    if (stats) k_raster<ROP, FMT, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
+    else k_raster<ROP, FMT, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
+  } while (0)
   if (rt_format == GS_PIX_RGBA16F) {
-    if (rop) k_raster<true, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, out, rt_pitch_bytes, opt.band_packed, stats);
-    else k_raster<false, GS_PIX_RGBA16F><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, out, rt_pitch_bytes, opt.band_packed, stats);
+    if (rop) GS_LAUNCH_RASTER(true, GS_PIX_RGBA16F); else GS_LAUNCH_RASTER(false, GS_PIX_RGBA16F);
   } else {
-    if (rop) k_raster<true, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, out, rt_pitch_bytes, opt.band_packed, stats);
-    else k_raster<false, GS_PIX_RGBA32F><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, out, rt_pitch_bytes, opt.band_packed, stats);
+    if (rop) GS_LAUNCH_RASTER(true, GS_PIX_RGBA32F); else GS_LAUNCH_RASTER(false, GS_PIX_RGBA32F);
   }
+#undef GS_LAUNCH_RASTER
 }
 
 uint32_t partition_own_bin_rows(const GsRenderOptions &opt, uint32_t binsY) { return make_partition(opt).own_rows_below(binsY); }
