@@ -182,10 +182,10 @@ GS_API int gs_composite(GsContext *ctx, const GsImage *rt, GsImage *camera_targe
  * camera_target != NULL].  do_sort == (m_FrameCounter % m_SortNthFrame == 0),
  * R/GaussianSplatRenderer.cs:120-121.  rt may be NULL when camera_target is given
  * (the RT then lives only in library scratch).
- * The fused path treats the colour of a splat that cannot produce a fragment (quad off screen, or
- * opacity below the 1/255 discard) as dead code: its _SplatViewData record keeps pos exactly, gets
- * colour = 0 and, when a cheap extent bound already puts it off screen, axes = 0.  Pixels are
- * unaffected; call gs_calc_view for the complete buffer. */
+ * In the reference _SplatViewData only carries CSCalcViewData's results to the draw call; the fused
+ * path hands them to its compositor directly and does NOT materialise that buffer (nor the colour of
+ * splats that cannot produce a fragment).  Pixels are unaffected; gs_readback_view after gs_frame
+ * returns GS_ERR_NOT_READY -- call gs_calc_view when the buffer itself is wanted. */
 GS_API int gs_frame(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp,
                     const GsRenderOptions *opt, int do_sort, GsImage *rt, GsImage *camera_target);
 

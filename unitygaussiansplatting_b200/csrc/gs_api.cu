@@ -57,7 +57,8 @@ struct GsAsset {
   void *d_pos = nullptr, *d_other = nullptr, *d_sh = nullptr, *d_color = nullptr, *d_chunks = nullptr;
   uint32_t *order = nullptr, *keys = nullptr, *key_table = nullptr, *view = nullptr, *rect = nullptr, *d_n = nullptr;
   float4 *draw = nullptr;  // raster-ready 48-byte records of the drawable splats
-  bool view_valid = false;
+  bool view_valid = false;   // the full 40-byte _SplatViewData buffer is current (gs_calc_view)
+  bool draw_valid = false;   // draw records + bin rects are current (gs_calc_view or gs_frame)
   uint32_t view_w = 0, view_h = 0;
 };
 
@@ -257,7 +258,8 @@ static int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const F
   launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, as->draw, cull, ctx->stream);
   rec(ctx, EV_VIEW1);
   ctx->launches += 1;
-  as->view_valid = true;
+  as->view_valid = !cull;
+  as->draw_valid = true;
   as->view_w = (uint32_t)fp->screen_w;
   as->view_h = (uint32_t)fp->screen_h;
   GS_CUDA_TRY(ctx, cudaGetLastError());
@@ -494,7 +496,7 @@ int gs_calc_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
 int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRenderOptions *opt_in, GsImage *rt) {
   int rc = check_params(ctx, as, fp);
   if (rc) return rc;
-  if (!as->view_valid || as->view_w != (uint32_t)fp->screen_w || as->view_h != (uint32_t)fp->screen_h)
+  if (!as->draw_valid || as->view_w != (uint32_t)fp->screen_w || as->view_h != (uint32_t)fp->screen_h)
     return fail(ctx, GS_ERR_NOT_READY, "gs_render needs gs_calc_view for the same screen size first");
   const uint32_t W = (uint32_t)fp->screen_w;
   uint32_t pitch = 0;
@@ -660,7 +662,7 @@ static int readback(GsAsset *as, void *dst, const void *src, size_t bytes) {
 int gs_readback_order(GsAsset *as, uint32_t *dst) { return readback(as, dst, as ? as->order : nullptr, as ? (size_t)as->av.n * 4 : 0); }
 int gs_readback_keys(GsAsset *as, uint32_t *dst) { return readback(as, dst, as ? as->keys : nullptr, as ? (size_t)as->av.n * 4 : 0); }
 int gs_readback_view(GsAsset *as, void *dst) {
-  if (as && !as->view_valid) return fail(as->ctx, GS_ERR_NOT_READY, "gs_calc_view has not run");
+  if (as && !as->view_valid) return fail(as->ctx, GS_ERR_NOT_READY, "_SplatViewData is only materialised by gs_calc_view (gs_frame hands the draw its own records)");
   return readback(as, dst, as ? as->view : nullptr, as ? (size_t)as->av.n * kViewStride : 0);
 }
 int gs_upload_order(GsAsset *as, const uint32_t *src) {

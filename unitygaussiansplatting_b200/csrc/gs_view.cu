@@ -197,11 +197,14 @@ __device__ __forceinline__ float3 operator+(float3 a, float3 b) { return make_fl
 __device__ __forceinline__ float3 operator-(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 neg(float3 a) { return make_float3(-a.x, -a.y, -a.z); }
 
-// CULL (used by the fused gs_frame): a splat whose quad cannot touch the screen, or whose opacity can never reach the
-// 1/255 discard threshold, is never drawn, so its colour half of the record (SH fetch + ShadeSH, 2/3 of the bytes and
-// ~half of the arithmetic) is dead code: the record then carries pos (and, unless even a cheap extent bound puts the
-// splat off screen, the axes) exactly, and colour = 0.  gs_calc_view (the
+// CULL (used by the fused gs_frame): in the reference _SplatViewData only carries CSCalcViewData's results to the draw.
+// The fused frame hands them over as 48-byte draw records instead, so (a) the 40-byte view record is a dead store and is
+// not written at all (245 MB/frame at 6.1 M splats), and (b) for a splat that can never produce a fragment -- quad off
+// screen, which a cheap extent bound often shows before any covariance maths, or opacity below the 1/255 discard -- the
+// colour half (SH fetch + ShadeSH, 2/3 of the bytes, ~half of the arithmetic) is dead code too.  gs_calc_view (the
 // stand-alone entry point) always runs the full kernel, so _SplatViewData parity is checked on that one.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int SHFMT, bool CULL>
 __global__ void __launch_bounds__(256)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
@@ -212,6 +215,16 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
   const bool chunked = blockIdx.x < a.chunkCount;
   if (chunked && threadIdx.x < 4)
     reinterpret_cast<uint4 *>(&s_chunk)[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(a.chunks + blockIdx.x) + threadIdx.x);
+  // the per-splat streams do not depend on the chunk header: start them before the barrier so the CTA pays one
+  // memory latency, not two (a CTA with nothing to draw was 2 dependent round trips long)
+  if (idx < a.n) {
+    prefetch_l1(a.pos + (uint64_t)idx * vec_stride(a.posFmt));
+    prefetch_l1(a.other + (uint64_t)idx * (4 + vec_stride(a.scaleFmt)));
+    if (!CULL) {
+      prefetch_l1(a.color + (uint64_t)splat_index_to_texel(idx) * (a.colFmt == 0 ? 16u : a.colFmt == 1 ? 8u : 4u));
+      if (fc.shOrder >= 1) prefetch_l1(a.sh + (uint64_t)idx * (SHFMT == 0 ? 192u : SHFMT == 1 ? 96u : SHFMT == 2 ? 60u : 32u));
+    }
+  }
   __syncthreads();
 
   uint32_t vw[10];
@@ -447,6 +460,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
     rect_out[idx] = rect;
   }
 
+  if (CULL) return;   // fused frame: the compositor reads the 48-byte draw records; _SplatViewData is not materialised
   // ---- coalesced store of the CTA's 256 x 40-byte records ----
 #pragma unroll
   for (int k = 0; k < 10; ++k) s_view[threadIdx.x * 10 + k] = vw[k];
