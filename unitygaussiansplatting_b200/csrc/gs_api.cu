@@ -229,6 +229,7 @@ static int upload_frame_inputs(GsContext *ctx, GsAsset *as, const GsFrameParams 
 static int check_params(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
   if (!ctx || !as || !fp) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "null context/asset/params");
   if (as->ctx != ctx) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "asset belongs to another context");
+  GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));   // the caller's current device may be another one
   if (!(fp->screen_w >= 1.0f) || !(fp->screen_h >= 1.0f) || fp->screen_w > 8160.0f || fp->screen_h > 8160.0f)
     return fail(ctx, GS_ERR_INVALID_ARGUMENT, "screen size must be in [1,8160] (8-bit bin indices)");
   if (fp->sh_order > 3) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "sh_order must be 0..3");
@@ -345,15 +346,24 @@ int gs_create(int cuda_device, void *stream_handle, GsContext **out) {
   GsContext *ctx = new (std::nothrow) GsContext();
   if (!ctx) return fail(nullptr, GS_ERR_OUT_OF_MEMORY, "host allocation failed");
   ctx->device = cuda_device;
-  GS_CUDA_TRY(ctx, cudaSetDevice(cuda_device));
-  if (stream_handle) ctx->stream = (cudaStream_t)stream_handle;
-  else { GS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
-  for (int i = 0; i < EV_COUNT; ++i) GS_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
-  GS_CUDA_TRY(ctx, cudaMalloc(&ctx->sort.ghist, 4 * 256 * 4));
-  GS_CUDA_TRY(ctx, cudaMalloc(&ctx->sort.tickets, 4 * 4));
-  GS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_scalar, 16 * 4));
-  GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.entry_count, 4 * 4));
-  GS_CUDA_TRY(ctx, cudaMemsetAsync(ctx->bin.entry_count, 0, 16, ctx->stream));
+  auto init = [&]() -> int {
+    GS_CUDA_TRY(ctx, cudaSetDevice(cuda_device));
+    if (stream_handle) ctx->stream = (cudaStream_t)stream_handle;
+    else { GS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    for (int i = 0; i < EV_COUNT; ++i) GS_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
+    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->sort.ghist, 4 * 256 * 4));
+    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->sort.tickets, 4 * 4));
+    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_scalar, 16 * 4));
+    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.entry_count, 4 * 4));
+    GS_CUDA_TRY(ctx, cudaMemsetAsync(ctx->bin.entry_count, 0, 16, ctx->stream));
+    return GS_OK;
+  };
+  const int rc = init();
+  if (rc != GS_OK) {
+    g_last_error = ctx->err;   // keep the text reachable through gs_last_error(NULL)
+    gs_destroy(ctx);
+    return rc;
+  }
   *out = ctx;
   return GS_OK;
 }
@@ -361,20 +371,21 @@ int gs_create(int cuda_device, void *stream_handle, GsContext **out) {
 void gs_destroy(GsContext *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->sort.alt_keys); cudaFree(ctx->sort.alt_vals); cudaFree(ctx->sort.lookback);
   cudaFree(ctx->sort.ghist); cudaFree(ctx->sort.tickets); cudaFree(ctx->d_scalar);
   cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
   cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted);
   for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 int gs_sync(GsContext *ctx) {
   if (!ctx) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "null context");
-  GS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  return GS_OK;
+  GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  // frames rendered into device images are not checked when they are enqueued: surface a truncated bin list here
+  return check_bin_overflow(ctx);
 }
 
 int gs_set_timing(GsContext *ctx, int enabled) {
