@@ -227,6 +227,49 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
   }
   __syncthreads();
 
+  if (CULL && chunked) {
+    // Hierarchical cull on the asset's own chunk bounds (free metadata: SplatChunkInfo pos min/max, scale max): if the
+    // chunk's box, grown by the largest screen reach any of its 256 splats can have, misses the screen -- or lies entirely
+    // behind the camera -- every splat of this CTA is undrawable and only its (empty) bin rect is written.
+    __shared__ int s_cull;
+    if (threadIdx.x < 32) {
+      const uint32_t l = threadIdx.x & 7;
+      const float bx = (l & 1) ? s_chunk.posX.y : s_chunk.posX.x, by = (l & 2) ? s_chunk.posY.y : s_chunk.posY.x,
+                  bz = (l & 4) ? s_chunk.posZ.y : s_chunk.posZ.x;
+      const float wx = fmaf(fc.o2w[2], bz, fmaf(fc.o2w[1], by, fmaf(fc.o2w[0], bx, fc.o2w[3])));
+      const float wy = fmaf(fc.o2w[6], bz, fmaf(fc.o2w[5], by, fmaf(fc.o2w[4], bx, fc.o2w[7])));
+      const float wz = fmaf(fc.o2w[10], bz, fmaf(fc.o2w[9], by, fmaf(fc.o2w[8], bx, fc.o2w[11])));
+      const float cxp = fmaf(fc.vp[2], wz, fmaf(fc.vp[1], wy, fmaf(fc.vp[0], wx, fc.vp[3])));
+      const float cyp = fmaf(fc.vp[6], wz, fmaf(fc.vp[5], wy, fmaf(fc.vp[4], wx, fc.vp[7])));
+      const float cwp = fmaf(fc.vp[14], wz, fmaf(fc.vp[13], wy, fmaf(fc.vp[12], wx, fc.vp[15])));
+      const bool behind = cwp <= 0.0f;   // clip.w is affine in position: its sign over the box is decided at the corners
+      const uint32_t nb = __ballot_sync(0xffffffffu, behind) & 0xffu;
+      bool cull = nb == 0xffu;
+      if (nb == 0u) {
+        const float iw = 1.0f / cwp;
+        float x0 = (cxp * iw * 0.5f + 0.5f) * fc.screenW, y0 = (0.5f - 0.5f * cyp * iw) * fc.screenH, x1 = x0, y1 = y0, wmin = cwp;
+#pragma unroll
+        for (int o = 4; o; o >>= 1) {
+          x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+          y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+          wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+        }
+        // largest decoded scale in the chunk: lerp(min,max,t)^8 <= max^8 for t in [0,1]; view depth |tz| >= wmin (w = -tz)
+        float sm = fmaxf(f16hi(s_chunk.sclX), fmaxf(f16hi(s_chunk.sclY), f16hi(s_chunk.sclZ)));
+        sm *= sm; sm *= sm; sm *= sm;
+        const float tr = fc.extentK * sm * sm / (wmin * wmin) + 0.6f;
+        const float reach = 4.04f * fminf(sqrtf(2.0f * tr), 4096.0f) + 2.0f;
+        cull = (x1 + reach < 0.0f) || (x0 - reach > fc.screenW) || (y1 + reach < 0.0f) || (y0 - reach > fc.screenH);
+      }
+      if (threadIdx.x == 0) s_cull = cull ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_cull) {
+      if (idx < a.n) rect_out[idx] = kRectEmpty;
+      return;
+    }
+  }
+
   uint32_t vw[10];
 #pragma unroll
   for (int k = 0; k < 10; ++k) vw[k] = 0;
