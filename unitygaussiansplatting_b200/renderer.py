@@ -99,18 +99,35 @@ def _image(arr, width: int, height: int) -> N.GsImage:
     return im
 
 
+_EYE4 = np.eye(4, dtype=np.float32)
+_inv_cache = {}
+
+
+def _inverse_cached(m: np.ndarray) -> np.ndarray:
+    """transform.worldToLocalMatrix: Unity keeps it alongside localToWorldMatrix; here it is cached per matrix value."""
+    key = m.tobytes()
+    hit = _inv_cache.get(key)
+    if hit is None:
+        if len(_inv_cache) > 64:
+            _inv_cache.clear()
+        hit = _inv_cache[key] = np.linalg.inv(m.astype(np.float64)).astype(np.float32)
+    return hit
+
+
 def make_frame_params(cam: Camera, localToWorld=None, splat_scale=1.0, opacity_scale=1.0, sh_order=3, sh_only=False, cutouts=None,
                       deleted_bits=None, splat_count=0):
     """The uniforms C# binds in CalcViewData / SortPoints (R/GaussianSplatRenderer.cs:586-606,617-631).
     Returns (GsFrameParams, keepalive list for the borrowed host pointers)."""
     fp = N.GsFrameParams()
-    o2w = np.eye(4, dtype=np.float32) if localToWorld is None else np.asarray(localToWorld, np.float32)
-    w2o = np.linalg.inv(o2w.astype(np.float64)).astype(np.float32)
-    for name, m in (("mat_object_to_world", o2w), ("mat_world_to_object", w2o), ("mat_view", cam.worldToCameraMatrix),
-                    ("mat_proj_gpu", cam.gpuProjectionMatrix(True))):
-        getattr(fp, name)[:] = colmajor(m).tolist()
+    o2w = _EYE4 if localToWorld is None else np.asarray(localToWorld, np.float32)
+    w2o = _inverse_cached(o2w)
+    for field, m in ((N.GsFrameParams.mat_object_to_world, o2w), (N.GsFrameParams.mat_world_to_object, w2o),
+                     (N.GsFrameParams.mat_view, cam.worldToCameraMatrix), (N.GsFrameParams.mat_proj_gpu, cam.gpuProjectionMatrix(True))):
+        cm = colmajor(m)   # 16 contiguous float32, UnityEngine.Matrix4x4 memory order
+        C.memmove(C.addressof(fp) + field.offset, cm.ctypes.data, 64)
     fp.screen_w, fp.screen_h = float(cam.pixelWidth), float(cam.pixelHeight)
-    fp.cam_pos_world[:] = [float(v) for v in np.asarray(cam.position, np.float32)]
+    pos = np.asarray(cam.position, np.float32)
+    fp.cam_pos_world[0], fp.cam_pos_world[1], fp.cam_pos_world[2] = float(pos[0]), float(pos[1]), float(pos[2])
     fp.splat_scale, fp.opacity_scale = float(splat_scale), float(opacity_scale)
     fp.sh_order, fp.sh_only = int(sh_order), 1 if sh_only else 0
     keep = []
