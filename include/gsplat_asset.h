@@ -58,6 +58,13 @@ GSA_API int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pos_fmt
                              uint32_t color_fmt, uint32_t sh_fmt, void *pos, void *other, void *color,
                              void *sh, void *chunks, float *bounds_out);
 
+/* INRIA .ply input: header parse + attribute mapping (E/Utils/PLYFileReader.cs:24-67,
+ * E/Utils/GaussianFileReader.cs:45-169), SH re-interleave (:183-205) and LinearizeData (:207-232).
+ * gsa_ply_vertex_count returns the vertex count (< 0: not a binary-little-endian gaussian-splat ply).
+ * gsa_ply_read fills `capacity` >= count records (already linearised, ready for gsa_create_asset). */
+GSA_API int64_t gsa_ply_vertex_count(const char *path);
+GSA_API int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity);
+
 /* Individual pieces, exposed for tests. */
 GSA_API uint64_t gsa_morton_encode3(uint32_t x, uint32_t y, uint32_t z);       /* R/GaussianUtils.cs:81-95 */
 GSA_API uint32_t gsa_splat_index_to_texture_index(uint32_t idx);              /* E/GaussianSplatAssetCreator.cs:863-871 */

@@ -134,3 +134,54 @@ def test_chunk_bounds_enclose_and_decode_is_inside_them(g, O):
         lo, hi = pos_minmax[i // 256, :, 0], pos_minmax[i // 256, :, 1]
         assert np.all(d["pos"] >= lo - 1e-6) and np.all(d["pos"] <= hi + 1e-6)
         assert 0.0 <= float(d["opacity"]) <= 1.0 and np.all(d["scale"] > 0)
+
+
+def _write_ply(path, cols, names, crlf=False, extra_uchar=False):
+    nl = "\r\n" if crlf else "\n"
+    n = cols.shape[0]
+    hdr = "ply" + nl + "format binary_little_endian 1.0" + nl + "element vertex %d" % n + nl
+    for nm in names:
+        hdr += "property float %s" % nm + nl
+    if extra_uchar:
+        hdr += "property uchar flag" + nl
+    hdr += "end_header" + nl
+    rec = np.zeros(n, dtype=[("f", "<f4", (len(names),))] + ([("u", "u1")] if extra_uchar else []))
+    rec["f"] = cols
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        f.write(rec.tobytes())
+
+
+def test_ply_reader_follows_the_importer(g, tmp_path):
+    """E/Utils/GaussianFileReader.cs:45-232: attribute mapping by name, SH re-interleave, LinearizeData."""
+    rng = np.random.default_rng(9)
+    names = ["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"] + ["f_rest_%d" % i for i in range(45)] + \
+            ["opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"]
+    n = 300
+    cols = rng.standard_normal((n, 62)).astype(np.float32)
+    perm = rng.permutation(62)                      # attribute order in the file is arbitrary: mapping is by name
+    _write_ply(tmp_path / "a.ply", cols[:, perm], [names[i] for i in perm], crlf=True, extra_uchar=True)
+    got = g.read_ply(tmp_path / "a.ply")
+    assert got.shape == (n, 62)
+    assert np.array_equal(got[:, 0:6], cols[:, 0:6])                                   # pos, normal untouched
+    assert np.allclose(got[:, 6:9], cols[:, 6:9] * 0.2820948 + 0.5, atol=1e-6)         # SH0ToColor
+    want_sh = cols[:, 9:54].reshape(n, 3, 15).transpose(0, 2, 1).reshape(n, 45)        # channel-major -> 15 x RGB
+    assert np.array_equal(got[:, 9:54], want_sh)
+    assert np.allclose(got[:, 54], 1 / (1 + np.exp(-cols[:, 54].astype(np.float64))), atol=1e-6)   # sigmoid
+    assert np.allclose(got[:, 55:58], np.exp(cols[:, 55:58].astype(np.float64)), rtol=1e-6)         # exp(log scale)
+    wxyz = cols[:, 58:62].astype(np.float64)
+    q = wxyz / np.linalg.norm(wxyz, axis=1, keepdims=True)
+    for i in range(0, n, 17):
+        R0 = _rotmat([q[i, 1], q[i, 2], q[i, 3], q[i, 0]])
+        R1 = _rotmat(_unpack_rot(got[i, 58:62].astype(np.float64)))
+        assert np.abs(R0 - R1).max() < 1e-5
+    # the records go straight into the packer
+    asset = g.create_asset(got.copy(), "Medium")
+    assert asset.splatCount == n
+    # missing required attribute / ascii ply -> rejected
+    _write_ply(tmp_path / "b.ply", cols[:, :61], names[:61])
+    with pytest.raises(ValueError):
+        g.read_ply(tmp_path / "b.ply")
+    (tmp_path / "c.ply").write_text("ply\nformat ascii 1.0\nelement vertex 1\nend_header\n")
+    with pytest.raises(ValueError):
+        g.read_ply(tmp_path / "c.ply")

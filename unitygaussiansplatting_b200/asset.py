@@ -98,6 +98,20 @@ def generate_input_splats(kind: int, n: int, seed: int) -> np.ndarray:
     return out
 
 
+def read_ply(path: str) -> np.ndarray:
+    """INRIA gaussian-splat .ply -> linearised InputSplatData records (n x 62 float32), as the reference importer reads
+    them (E/Utils/GaussianFileReader.cs:45-232)."""
+    lib = N.asset_lib()
+    n = lib.gsa_ply_vertex_count(str(path).encode())
+    if n < 0:
+        raise ValueError("%s is not a binary little-endian gaussian splat PLY (code %d)" % (path, n))
+    out = np.empty((n, INPUT_SPLAT_FLOATS), np.float32)
+    rc = lib.gsa_ply_read(str(path).encode(), out.ctypes.data, n)
+    if rc != 0:
+        raise ValueError("gsa_ply_read failed (%d)" % rc)
+    return out
+
+
 def create_asset(splats: np.ndarray, quality: str = "Medium", formats=None) -> GaussianSplatAsset:
     """CreateAsset: Morton reorder, chunking, packing.  `splats` (n x 62 float32) is consumed."""
     pf, sf, cf, shf = formats if formats is not None else QUALITY[quality]

@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <cstdio>
+#include <string>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -436,6 +438,128 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
       t[15] = 0;
       std::memcpy(h, t, 32);
     }
+  }
+  return 0;
+}
+
+
+// ---- INRIA .ply reader (E/Utils/PLYFileReader.cs, E/Utils/GaussianFileReader.cs) --------------------------------
+namespace {
+struct PlyHeader {
+  int64_t count = -1;
+  uint32_t stride = 0;
+  bool binary_le = false;
+  std::vector<std::pair<std::string, int>> attrs;  // name, size in bytes (4 float, 8 double, 1 uchar, 0 unknown)
+  std::vector<bool> is_float;
+  long data_offset = 0;
+};
+
+bool read_line(FILE *f, std::string &line) {
+  line.clear();
+  int c;
+  bool any = false;
+  while ((c = fgetc(f)) != EOF) {
+    any = true;
+    if (c == '\n') break;
+    line.push_back((char)c);
+  }
+  if (!line.empty() && line.back() == '\r') line.pop_back();  // CRLF
+  return any;
+}
+
+bool parse_ply_header(FILE *f, PlyHeader &h) {
+  std::string line;
+  for (int i = 0; i < 9000; ++i) {  // kMaxHeaderLines
+    if (!read_line(f, line) || line == "end_header" || line.empty()) break;
+    char a[64], b[64], c[64];
+    if (sscanf(line.c_str(), "%63s %63s %63s", a, b, c) != 3) continue;
+    const std::string t0 = a, t1 = b, t2 = c;
+    if (t0 == "format" && t1 == "binary_little_endian" && t2 == "1.0") h.binary_le = true;
+    if (t0 == "element" && t1 == "vertex") h.count = atoll(c);
+    if (t0 == "property") {
+      const int size = t1 == "float" ? 4 : t1 == "double" ? 8 : t1 == "uchar" ? 1 : 0;
+      h.stride += size;
+      h.attrs.push_back({t2, size});
+      h.is_float.push_back(t1 == "float");
+    }
+  }
+  h.data_offset = ftell(f);
+  return h.binary_le && h.count >= 0;
+}
+
+const char *kSplatAttrs[62] = {
+    "x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2",
+    "f_rest_0", "f_rest_1", "f_rest_2", "f_rest_3", "f_rest_4", "f_rest_5", "f_rest_6", "f_rest_7", "f_rest_8", "f_rest_9",
+    "f_rest_10", "f_rest_11", "f_rest_12", "f_rest_13", "f_rest_14", "f_rest_15", "f_rest_16", "f_rest_17", "f_rest_18", "f_rest_19",
+    "f_rest_20", "f_rest_21", "f_rest_22", "f_rest_23", "f_rest_24", "f_rest_25", "f_rest_26", "f_rest_27", "f_rest_28", "f_rest_29",
+    "f_rest_30", "f_rest_31", "f_rest_32", "f_rest_33", "f_rest_34", "f_rest_35", "f_rest_36", "f_rest_37", "f_rest_38", "f_rest_39",
+    "f_rest_40", "f_rest_41", "f_rest_42", "f_rest_43", "f_rest_44",
+    "opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"};
+const char *kRequired[14] = {"x", "y", "z", "f_dc_0", "f_dc_1", "f_dc_2", "opacity", "scale_0", "scale_1", "scale_2",
+                             "rot_0", "rot_1", "rot_2", "rot_3"};
+}  // namespace
+
+int64_t gsa_ply_vertex_count(const char *path) {
+  FILE *f = path ? fopen(path, "rb") : nullptr;
+  if (!f) return -1;
+  PlyHeader h;
+  const bool ok = parse_ply_header(f, h);
+  fclose(f);
+  if (!ok) return -2;
+  for (const char *req : kRequired) {  // CheckPLYAttributes, GaussianFileReader.cs:73-80
+    bool found = false;
+    for (size_t i = 0; i < h.attrs.size(); ++i) found |= h.attrs[i].first == req && h.is_float[i];
+    if (!found) return -3;
+  }
+  return h.count;
+}
+
+int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity) {
+  const int64_t n = gsa_ply_vertex_count(path);
+  if (n < 0) return (int)n;
+  if (!out || (uint64_t)n > capacity) return -1;
+  FILE *f = fopen(path, "rb");
+  if (!f) return -1;
+  PlyHeader h;
+  parse_ply_header(f, h);
+  std::vector<int> src_off(62, -1);  // PLYDataToSplats, GaussianFileReader.cs:82-169
+  {
+    int off = 0;
+    for (size_t i = 0; i < h.attrs.size(); ++i) {
+      if (h.is_float[i])
+        for (int k = 0; k < 62; ++k)
+          if (h.attrs[i].first == kSplatAttrs[k] && src_off[k] < 0) src_off[k] = off;
+      off += h.attrs[i].second;
+    }
+  }
+  std::vector<uint8_t> raw((size_t)n * h.stride);
+  fseek(f, h.data_offset, SEEK_SET);
+  const size_t got = fread(raw.data(), 1, raw.size(), f);
+  fclose(f);
+  if (got != raw.size()) return -4;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    float d[62];
+    const uint8_t *src = raw.data() + (size_t)i * h.stride;
+    for (int k = 0; k < 62; ++k) {
+      d[k] = 0.0f;
+      if (src_off[k] >= 0) std::memcpy(&d[k], src + src_off[k], 4);
+    }
+    // ReorderSHs: f_rest is channel-major (15 R, 15 G, 15 B) -> 15 x RGB  (:183-205)
+    float tmp[45];
+    for (int j = 0; j < 15; ++j) { tmp[j * 3] = d[9 + j]; tmp[j * 3 + 1] = d[9 + j + 15]; tmp[j * 3 + 2] = d[9 + j + 30]; }
+    std::memcpy(&d[9], tmp, sizeof(tmp));
+    GsaInputSplat s;
+    std::memcpy(&s, d, sizeof(s));
+    // LinearizeData (:207-232): rot_0..3 = (w,x,y,z) -> normalise -> (x,y,z,w) -> smallest-three
+    float q[4] = {s.rot[0], s.rot[1], s.rot[2], s.rot[3]};
+    const float len = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float qn[4] = {q[1] / len, q[2] / len, q[3] / len, q[0] / len};  // math.normalize(wxyz).yzwx
+    pack_smallest3(qn, s.rot);
+    for (int k = 0; k < 3; ++k) s.scale[k] = std::fabs(std::exp(s.scale[k]));      // LinearScale
+    for (int k = 0; k < 3; ++k) s.dc0[k] = s.dc0[k] * 0.2820948f + 0.5f;           // SH0ToColor
+    s.opacity = 1.0f / (1.0f + std::exp(-s.opacity));                               // Sigmoid
+    out[i] = s;
   }
   return 0;
 }
