@@ -77,7 +77,10 @@ def render_partitioned(renderer, cam, part: BandPartition, gathered, out_image, 
     mine = gathered[part.index]
     renderer.partition = part.options()
     renderer.band_packed = True
-    renderer.SortAndRenderSplats(cam, rt=mine[:own_px])
+    if own_px:
+        renderer.SortAndRenderSplats(cam, rt=mine[:own_px])
+    else:   # more partitions than 64-pixel rows: nothing to composite here, but keep the draw order current
+        renderer.SortPoints(cam)
     if part.count > 1:
         dist.all_gather_into_tensor(gathered.view(-1), mine.reshape(-1))   # in place: input is our slice of the output
     unshuffle(renderer.context, gathered, part, out_image)
