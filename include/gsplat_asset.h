@@ -65,6 +65,11 @@ GSA_API int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pos_fmt
 GSA_API int64_t gsa_ply_vertex_count(const char *path);
 GSA_API int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity);
 
+/* Niantic/Scaniverse .spz input (gzip stream, version 2; E/Utils/SPZFileReader.cs:20-195): same contract as the
+ * ply pair above.  Unlike PLY the records need no LinearizeData pass: the unpack already yields linear values. */
+GSA_API int64_t gsa_spz_vertex_count(const char *path);
+GSA_API int gsa_spz_read(const char *path, GsaInputSplat *out, uint32_t capacity);
+
 /* Individual pieces, exposed for tests. */
 GSA_API uint64_t gsa_morton_encode3(uint32_t x, uint32_t y, uint32_t z);       /* R/GaussianUtils.cs:81-95 */
 GSA_API uint32_t gsa_splat_index_to_texture_index(uint32_t idx);              /* E/GaussianSplatAssetCreator.cs:863-871 */

@@ -185,3 +185,42 @@ def test_ply_reader_follows_the_importer(g, tmp_path):
     (tmp_path / "c.ply").write_text("ply\nformat ascii 1.0\nelement vertex 1\nend_header\n")
     with pytest.raises(ValueError):
         g.read_ply(tmp_path / "c.ply")
+
+
+def test_spz_reader_follows_the_importer(g, tmp_path):
+    """E/Utils/SPZFileReader.cs:66-195: gzip stream, 24-bit fixed-point positions, byte-quantised everything else."""
+    import gzip
+    import struct
+    rng = np.random.default_rng(10)
+    n, sh_level, fract = 257, 2, 12
+    shc = 8
+    pos = rng.integers(-2**23, 2**23, (n, 3), dtype=np.int64)
+    alpha = rng.integers(0, 256, n, dtype=np.uint8)
+    col = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    scale = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    rot = rng.integers(60, 196, (n, 3), dtype=np.uint8)
+    sh = rng.integers(0, 256, (n, shc * 3), dtype=np.uint8)
+    p24 = np.zeros((n, 3, 3), np.uint8)
+    u = pos & 0xFFFFFF
+    p24[..., 0], p24[..., 1], p24[..., 2] = u & 255, (u >> 8) & 255, (u >> 16) & 255
+    blob = struct.pack("<IIII", 0x5053474E, 2, n, sh_level | (fract << 8)) + p24.tobytes() + alpha.tobytes() + col.tobytes() + \
+        scale.tobytes() + rot.tobytes() + sh.tobytes()
+    with gzip.open(tmp_path / "a.spz", "wb") as f:
+        f.write(blob)
+    got = g.read_spz(tmp_path / "a.spz")
+    assert got.shape == (n, 62)
+    assert np.array_equal(got[:, 0:3], (pos.astype(np.float32) * np.float32(1.0 / (1 << fract))))
+    assert np.allclose(got[:, 55:58], np.exp(scale.astype(np.float64) / 16.0 - 10.0), rtol=2e-6)
+    assert np.array_equal(got[:, 54], alpha.astype(np.float32) / np.float32(255.0))
+    assert np.allclose(got[:, 6:9], ((col / 255.0 - 0.5) / 0.15) * 0.2820948 + 0.5, atol=2e-6)
+    assert np.array_equal(got[:, 9:9 + shc * 3], (sh.astype(np.float32) - 128.0) / 128.0) and not got[:, 9 + shc * 3:54].any()
+    xyz = rot.astype(np.float64) / 127.5 - 1.0
+    w = np.sqrt(np.maximum(0.0, 1.0 - (xyz ** 2).sum(1)))
+    for i in range(0, n, 13):
+        q = np.array([xyz[i, 0], xyz[i, 1], xyz[i, 2], w[i]]); q /= np.linalg.norm(q)
+        assert np.abs(_rotmat(q) - _rotmat(_unpack_rot(got[i, 58:62].astype(np.float64)))).max() < 1e-5
+    g.create_asset(got.copy(), "Medium")
+    with gzip.open(tmp_path / "b.spz", "wb") as f:
+        f.write(struct.pack("<IIII", 0x5053474E, 3, n, 0))        # unsupported version
+    with pytest.raises(ValueError):
+        g.read_spz(tmp_path / "b.spz")

@@ -112,6 +112,8 @@ ASSET_SYMBOLS = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsa_ply_vertex_count": (C.c_int64, [C.c_char_p]),
     "gsa_ply_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint32]),
+    "gsa_spz_vertex_count": (C.c_int64, [C.c_char_p]),
+    "gsa_spz_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint32]),
     "gsa_morton_encode3": (C.c_uint64, [C.c_uint32, C.c_uint32, C.c_uint32]),
     "gsa_splat_index_to_texture_index": (C.c_uint32, [C.c_uint32]),
     "gsa_pack_smallest3": (None, [C.c_void_p, C.c_void_p]),

@@ -112,6 +112,19 @@ def read_ply(path: str) -> np.ndarray:
     return out
 
 
+def read_spz(path: str) -> np.ndarray:
+    """Niantic/Scaniverse .spz -> InputSplatData records, as E/Utils/SPZFileReader.cs unpacks them."""
+    lib = N.asset_lib()
+    n = lib.gsa_spz_vertex_count(str(path).encode())
+    if n < 0:
+        raise ValueError("%s is not a version-2 SPZ file (code %d)" % (path, n))
+    out = np.empty((n, INPUT_SPLAT_FLOATS), np.float32)
+    rc = lib.gsa_spz_read(str(path).encode(), out.ctypes.data, n)
+    if rc != 0:
+        raise ValueError("gsa_spz_read failed (%d)" % rc)
+    return out
+
+
 def create_asset(splats: np.ndarray, quality: str = "Medium", formats=None) -> GaussianSplatAsset:
     """CreateAsset: Morton reorder, chunking, packing.  `splats` (n x 62 float32) is consumed."""
     pf, sf, cf, shf = formats if formats is not None else QUALITY[quality]

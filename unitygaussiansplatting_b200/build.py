@@ -81,7 +81,7 @@ def build_asset(force: bool = False) -> Path:
     src = CSRC / "asset_creator.cpp"
     if force or _stale(ASSET_LIB, [src, ROOT / "include" / "gsplat_asset.h"]):
         _run([_host_cxx(), "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",
-              "-o", str(ASSET_LIB), str(src)])
+              "-o", str(ASSET_LIB), str(src), "-lz"])
     return ASSET_LIB
 
 

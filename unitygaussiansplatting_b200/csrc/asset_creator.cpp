@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <zlib.h>
+
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -559,6 +561,85 @@ int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity) {
     for (int k = 0; k < 3; ++k) s.scale[k] = std::fabs(std::exp(s.scale[k]));      // LinearScale
     for (int k = 0; k < 3; ++k) s.dc0[k] = s.dc0[k] * 0.2820948f + 0.5f;           // SH0ToColor
     s.opacity = 1.0f / (1.0f + std::exp(-s.opacity));                               // Sigmoid
+    out[i] = s;
+  }
+  return 0;
+}
+
+
+// ---- Niantic .spz reader (E/Utils/SPZFileReader.cs) -----------------------------------------------------------
+namespace {
+struct SpzHeader { uint32_t magic, version, numPoints, sh_fracbits_flags_reserved; };
+int spz_open(const char *path, gzFile *gz, SpzHeader *h) {
+  *gz = path ? gzopen(path, "rb") : nullptr;
+  if (!*gz) return -1;
+  if (gzread(*gz, h, 16) != 16 || h->magic != 0x5053474eu || h->version != 2u) { gzclose(*gz); return -2; }   // :38-47
+  return 0;
+}
+}  // namespace
+
+int64_t gsa_spz_vertex_count(const char *path) {
+  gzFile gz;
+  SpzHeader h;
+  const int rc = spz_open(path, &gz, &h);
+  if (rc) return rc;
+  gzclose(gz);
+  return (int64_t)h.numPoints;
+}
+
+int gsa_spz_read(const char *path, GsaInputSplat *out, uint32_t capacity) {
+  gzFile gz;
+  SpzHeader h;
+  int rc = spz_open(path, &gz, &h);
+  if (rc) return rc;
+  const int64_t n = h.numPoints;
+  const int shLevel = (int)(h.sh_fracbits_flags_reserved & 0xFF), fractBits = (int)((h.sh_fracbits_flags_reserved >> 8) & 0xFF);
+  if (n < 1 || n > 10000000 || shLevel < 0 || shLevel > 3 || fractBits < 0 || fractBits > 24 || !out || (uint64_t)n > capacity) {  // :70-75
+    gzclose(gz);
+    return -3;
+  }
+  const int shCoeffs = shLevel == 1 ? 3 : shLevel == 2 ? 8 : shLevel == 3 ? 15 : 0;  // :54-64
+  std::vector<uint8_t> pos((size_t)n * 9), alpha((size_t)n), col((size_t)n * 3), scale((size_t)n * 3), rot((size_t)n * 3),
+      sh((size_t)n * 3 * shCoeffs);
+  auto rd = [&](std::vector<uint8_t> &v) {   // gzread takes an unsigned int length: read in slices
+    size_t done = 0;
+    while (done < v.size()) {
+      const unsigned want = (unsigned)std::min<size_t>(v.size() - done, 1u << 30);
+      const int got = gzread(gz, v.data() + done, want);
+      if (got <= 0) return false;
+      done += (size_t)got;
+    }
+    return true;
+  };
+  const bool ok = rd(pos) && rd(alpha) && rd(col) && rd(scale) && rd(rot) && rd(sh);  // stream order, :87-93
+  gzclose(gz);
+  if (!ok) return -4;
+  const float fractScale = 1.0f / (float)(1 << fractBits);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {  // UnpackDataJob, :125-195
+    GsaInputSplat s;
+    std::memset(&s, 0, sizeof(s));
+    for (int k = 0; k < 3; ++k) {
+      const size_t b = ((size_t)i * 3 + k) * 3;
+      int32_t fx = pos[b] | (pos[b + 1] << 8) | (pos[b + 2] << 16);
+      if (fx & 0x800000) fx |= (int32_t)0xff000000;   // 24-bit sign extension
+      s.pos[k] = (float)fx * fractScale;
+      s.scale[k] = std::fabs(std::exp((float)scale[(size_t)i * 3 + k] / 16.0f - 10.0f));
+    }
+    const float x = (float)rot[(size_t)i * 3] * (1.0f / 127.5f) - 1.0f, y = (float)rot[(size_t)i * 3 + 1] * (1.0f / 127.5f) - 1.0f,
+                z = (float)rot[(size_t)i * 3 + 2] * (1.0f / 127.5f) - 1.0f;
+    const float w = std::sqrt(std::max(0.0f, 1.0f - (x * x + y * y + z * z)));
+    const float len = std::sqrt(x * x + y * y + z * z + w * w);
+    const float q[4] = {x / len, y / len, z / len, w / len};
+    pack_smallest3(q, s.rot);
+    s.opacity = (float)alpha[(size_t)i] / 255.0f;
+    for (int k = 0; k < 3; ++k) {
+      float c = (float)col[(size_t)i * 3 + k] / 255.0f - 0.5f;
+      c /= 0.15f;
+      s.dc0[k] = c * 0.2820948f + 0.5f;   // SH0ToColor
+    }
+    const size_t shIdx = (size_t)i * shCoeffs * 3;
+    for (int j = 0; j < shCoeffs * 3; ++j) s.sh[j] = ((float)sh[shIdx + j] - 128.0f) / 128.0f;
     out[i] = s;
   }
   return 0;
