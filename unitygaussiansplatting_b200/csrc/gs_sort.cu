@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d) {
 
 // ---- one digit pass -------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t gtime() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define GS_TRACE(slot) do { if (trace > (uint64_t *)1 && tid == 0) trace[(size_t)tile * 8 + (slot)] = gtime(); } while (0)
+#define GS_TRACE(slot) do { if (trace && tid == 0) trace[(size_t)tile * 8 + (slot)] = gtime(); } while (0)
 
 // GATHER: the keys of this pass are keys_src[payload] (pass 0 of the depth sort reads the per-splat key
 // table through last frame's order, S/SplatUtilities.compute:76-81, without a separate gather pass).
@@ -351,8 +351,7 @@ void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, 
   }
   for (int p = 0; p < passes; ++p) {
     uint64_t *trace = (trace_path && passes == 4 && p == 1) ? g_trace : nullptr;
-    if (getenv("GS_SORT_NOLOOKBACK")) trace = (uint64_t *)1;
-    if (trace > (uint64_t *)1) cudaMemsetAsync(trace, 0, (size_t)tiles * 8 * sizeof(uint64_t), s);
+    if (trace) cudaMemsetAsync(trace, 0, (size_t)tiles * 8 * sizeof(uint64_t), s);
     if (pass_events) cudaEventRecord(pass_events[p], s);
     uint32_t *lb = sc.lookback + (size_t)p * tiles * nb;
     const bool gather = key_table != nullptr && p == 0;   // pass 0 reads key_table[vals[i]] instead of keys[i]
