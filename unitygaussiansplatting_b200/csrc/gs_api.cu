@@ -59,6 +59,7 @@ struct GsAsset {
   float4 *draw = nullptr;  // raster-ready 48-byte records of the drawable splats
   bool view_valid = false;   // the full 40-byte _SplatViewData buffer is current (gs_calc_view)
   bool draw_valid = false;   // draw records + bin rects are current (gs_calc_view or gs_frame)
+  uint32_t draw_part[3] = {0, 0, 1};   // the tile partition those records were culled for (count <= 1: complete)
   uint32_t view_w = 0, view_h = 0;
 };
 
@@ -252,15 +253,25 @@ static int do_sort(GsContext *ctx, GsAsset *as, const FrameConsts &fc) {
   return GS_OK;
 }
 
-static int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameConsts &fc, bool cull) {
+static GsRenderOptions default_opts() {
+  GsRenderOptions o;
+  memset(&o, 0, sizeof(o));
+  return o;
+}
+
+static int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameConsts &fc, bool cull, const GsRenderOptions &opt) {
   int rc = upload_frame_inputs(ctx, as, fp);
   if (rc) return rc;
   rec(ctx, EV_VIEW0);
-  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, as->draw, cull, ctx->stream);
+  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, as->draw, cull, make_partition(opt), ctx->stream);
   rec(ctx, EV_VIEW1);
   ctx->launches += 1;
   as->view_valid = !cull;
   as->draw_valid = true;
+  {
+    const gs::Partition p = make_partition(opt);
+    as->draw_part[0] = p.index; as->draw_part[1] = cull ? p.count : 0; as->draw_part[2] = p.band;
+  }
   as->view_w = (uint32_t)fp->screen_w;
   as->view_h = (uint32_t)fp->screen_h;
   GS_CUDA_TRY(ctx, cudaGetLastError());
@@ -298,11 +309,6 @@ static int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const G
   return GS_OK;
 }
 
-static GsRenderOptions default_opts() {
-  GsRenderOptions o;
-  memset(&o, 0, sizeof(o));
-  return o;
-}
 
 static int image_ok(GsContext *ctx, const GsImage *im, uint32_t W, uint32_t H, uint32_t *pitch) {
   if (!im || !im->data) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "image is null");
@@ -501,7 +507,7 @@ int gs_calc_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
   if (rc) return rc;
   for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
   FrameConsts fc = make_frame_consts(fp);
-  return do_view(ctx, as, fp, fc, false);
+  return do_view(ctx, as, fp, fc, false, default_opts());
 }
 
 int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRenderOptions *opt_in, GsImage *rt) {
@@ -513,6 +519,11 @@ int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRend
   uint32_t pitch = 0;
   GsRenderOptions opt = opt_in ? *opt_in : default_opts();
   if (opt.blend_mode > GS_BLEND_FP32) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad blend mode");
+  {
+    const gs::Partition p = make_partition(opt);
+    if (as->draw_part[1] > 1 && (as->draw_part[0] != p.index || as->draw_part[1] != p.count || as->draw_part[2] != p.band))
+      return fail(ctx, GS_ERR_NOT_READY, "the last gs_frame prepared draw records for another tile partition; run gs_calc_view");
+  }
   FrameConsts fc = make_frame_consts(fp);
   const uint32_t H = opt.band_packed ? partition_own_bin_rows(opt, fc.binsY) * kBin : (uint32_t)fp->screen_h;
   if ((rc = image_ok(ctx, rt, W, H, &pitch))) return rc;
@@ -577,7 +588,7 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
   if (rt) { if ((rc = image_ok(ctx, rt, W, H, &rt_pitch))) return rc; rt_fmt = rt->format; }
   for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
   if (do_sort_flag && (rc = do_sort(ctx, as, fc))) return rc;
-  if ((rc = do_view(ctx, as, fp, fc, true))) return rc;   // fused frame: colour of never-drawn splats is dead code
+  if ((rc = do_view(ctx, as, fp, fc, true, opt))) return rc;   // fused frame: colour of never-drawn splats is dead code
   void *d_rt;
   uint32_t d_pitch;
   const bool rt_dev = rt && rt->memory == GS_MEM_DEVICE;

@@ -48,11 +48,43 @@ __device__ __forceinline__ uint32_t footprint_tile_rect(const SplatFootprint &fp
   return tx0 | (ty0 << 8) | (tx1 << 16) | (ty1 << 24);
 }
 
+// ---- screen-tile partition helpers (multi-GPU bands) ---------------------------
+struct Partition {
+  uint32_t index, count, band;  // count <= 1: everything is ours
+  __host__ __device__ uint32_t own_rows_below(uint32_t y) const {  // # own tile rows in [0, y)
+    if (count <= 1) return y;
+    uint32_t cyc = band * count, q = y / cyc, r = y % cyc;
+    uint32_t lo = index * band;
+    uint32_t in = r > lo ? (r - lo < band ? r - lo : band) : 0u;
+    return q * band + in;
+  }
+  __host__ __device__ bool owns(uint32_t y) const { return count <= 1 || (y / band) % count == index; }
+  __host__ __device__ uint32_t kth_own_row(uint32_t k) const {
+    if (count <= 1) return k;
+    return ((k / band) * count + index) * band + (k % band);
+  }
+};
+inline Partition make_partition(const GsRenderOptions &o) {
+  Partition p;
+  p.count = o.partition_count;
+  p.index = o.partition_count > 1 ? o.partition_index : 0;
+  p.band = o.band_rows ? o.band_rows : 1;
+  return p;
+}
+
+__device__ __forceinline__ uint32_t rect_entries(uint32_t r, const Partition &p) {
+  if (r == kRectEmpty) return 0;
+  uint32_t x0 = r & 255u, y0 = (r >> 8) & 255u, x1 = (r >> 16) & 255u, y1 = r >> 24;
+  uint32_t rows = p.own_rows_below(y1 + 1) - p.own_rows_below(y0);
+  return rows * (x1 - x0 + 1);
+}
+
+
 // ---- launchers (each enqueues on `s`, returns nothing; errors surface via cudaGetLastError) ----
 void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s);
 void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s);
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                      uint32_t *rect, float4 *draw, bool cull_undrawable, cudaStream_t s);
+                      uint32_t *rect, float4 *draw, bool cull_undrawable, const Partition &part, cudaStream_t s);
 
 // Radix sort (gs_sort.cu).  Scratch layout is owned by the caller (gs_api.cu).
 struct SortScratch {

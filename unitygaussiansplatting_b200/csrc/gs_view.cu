@@ -208,7 +208,7 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 template <int SHFMT, bool CULL>
 __global__ void __launch_bounds__(256)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
-            uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out) {
+            uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out, Partition part) {
   __shared__ __align__(16) uint32_t s_view[256 * 10];
   __shared__ __align__(16) Chunk s_chunk;
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
@@ -448,7 +448,9 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
         // can the +-2 quad touch a pixel centre at all?  (65000 = the largest opacity CSCalcViewData can emit: the
         // visible part is then the whole quad; a smaller opacity only shrinks it)
         SplatFootprint g0;
-        drawable = splat_footprint(clip, a1x, a1y, a2x, a2y, 65000.0f, fc.screenW, fc.screenH, g0) && footprint_tile_rect(g0, fc) != kRectEmpty;
+        // (multi-GPU: ... or only rows of other ranks' bands -- then its colour is somebody else's job)
+        drawable = splat_footprint(clip, a1x, a1y, a2x, a2y, 65000.0f, fc.screenW, fc.screenH, g0) &&
+                   rect_entries(footprint_tile_rect(g0, fc), part) != 0;
         if (drawable) {
           load_color();
           finish_color();
@@ -535,21 +537,21 @@ void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *
 
 template <bool CULL>
 static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                               uint32_t *rect, float4 *draw, cudaStream_t s) {
+                               uint32_t *rect, float4 *draw, const Partition &part, cudaStream_t s) {
   const uint32_t grid = (a.n + 255) / 256;
   switch (a.shFmt) {
-    case 0: k_calc_view<0, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw); break;
-    case 1: k_calc_view<1, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw); break;
-    case 2: k_calc_view<2, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw); break;
-    default: k_calc_view<3, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw); break;
+    case 0: k_calc_view<0, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part); break;
+    case 1: k_calc_view<1, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part); break;
+    case 2: k_calc_view<2, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part); break;
+    default: k_calc_view<3, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part); break;
   }
 }
 
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                      uint32_t *rect, float4 *draw, bool cull_undrawable, cudaStream_t s) {
+                      uint32_t *rect, float4 *draw, bool cull_undrawable, const Partition &part, cudaStream_t s) {
   if (!a.n) return;
-  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, view, rect, draw, s);
-  else launch_calc_view_t<false>(a, fc, cutouts, deleted, view, rect, draw, s);
+  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, view, rect, draw, part, s);
+  else launch_calc_view_t<false>(a, fc, cutouts, deleted, view, rect, draw, part, s);
 }
 
 }  // namespace gs
