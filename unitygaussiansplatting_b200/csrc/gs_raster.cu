@@ -248,7 +248,32 @@ __global__ void __launch_bounds__(1024) k_tile_order(const uint32_t *__restrict_
   for (uint32_t t = threadIdx.x; t < ntiles; t += 1024) order[atomicAdd(&s_base[63u - bucket(cost[t])], 1u)] = t;
 }
 
-template <bool FP16_ROP, int OUT_FMT, bool STATS>
+// ---- TMA (bulk async copy) staging: one 48-byte cp.async.bulk per record, completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "GS_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra GS_DONE;\n\t"
+      "bra GS_WAIT;\n\t"
+      "GS_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool FP16_ROP, int OUT_FMT, bool STATS, bool TMA>
 __global__ void __launch_bounds__(256)
 k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const uint2 *__restrict__ bin_ranges,
          const uint32_t *__restrict__ tile_vals, const uint32_t *__restrict__ tile_order, uint32_t *__restrict__ tile_cost, uint32_t ntx,
@@ -256,8 +281,20 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   uint32_t st_batches = 0, st_culls = 0, st_cand = 0, st_eval = 0, st_blend = 0;   // GS_RASTER_STATS diagnostics (per warp)
   unsigned long long st_t0 = 0;
   if (STATS) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(st_t0));
-  // two staging buffers of 256 raster records (3 x float4 each): batch k+1 lands by cp.async while batch k is composited
-  __shared__ float4 s_rec[2][3][256];  // [buf][0]: cx, cy, i1x, i1y   [1]: i2x, i2y, opacity, hx   [2]: r, g, b, hy
+  // two staging buffers of 256 raster records (3 x float4 each): batch k+1 lands asynchronously while batch k is composited.
+  // cp.async path: planar [buf][plane][entry]; TMA path: the 48-byte records as they are, [buf][entry][plane].
+  __shared__ __align__(128) float4 s_rec[2][3][256];  // plane 0: cx, cy, i1x, i1y   1: i2x, i2y, opacity, hx   2: r, g, b, hy
+  __shared__ __align__(8) uint64_t s_bar[2];
+  constexpr int ES = TMA ? 3 : 1;     // float4 stride between consecutive entries of one plane
+  constexpr int PS = TMA ? 1 : 256;   // float4 stride between the planes of one entry
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar[0], 256);
+      mbar_init(&s_bar[1], 256);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // grid: x = 16-pixel tile column, y = 2 * (own 32-pixel bin row) + (upper | lower tile row of that bin row)
@@ -283,6 +320,17 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   // three-deep pipeline: splat ids of batch k+2 (register) -> records of batch k+1 (cp.async in flight) -> batch k (composited)
   auto load_id = [&](uint32_t e) -> uint32_t { return e < range.y ? __ldg(tile_vals + e) : 0xFFFFFFFFu; };
   auto stage = [&](int buf, uint32_t id) {
+    float4 *base_f4 = &s_rec[buf][0][0];
+    if (TMA) {
+      // every thread arrives once per stage; a thread with a record first announces its 48 bytes, then issues the bulk copy
+      if (id != 0xFFFFFFFFu) {
+        mbar_arrive_expect_tx(&s_bar[buf], 48u);
+        bulk_copy_g2s(base_f4 + (size_t)tid * 3, draw + (size_t)id * 3, 48u, &s_bar[buf]);
+      } else {
+        mbar_arrive(&s_bar[buf]);
+      }
+      return;
+    }
     if (id != 0xFFFFFFFFu) {
       const float4 *src = draw + (size_t)id * 3;
       cp_async16(&s_rec[buf][0][tid], src);
@@ -293,15 +341,21 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   };
   uint32_t id_next = load_id(range.x + tid);
   stage(0, id_next);
+  uint32_t issued = 0;   // index of the newest stage handed to the copy engine
   id_next = load_id(range.x + 256 + tid);
 
   int buf = 0;
-  for (uint32_t base = range.x; base < range.y; base += 256, buf ^= 1) {
-    stage(buf ^ 1, id_next);                       // batch k+1 -> other buffer (free since the barrier that ended batch k-1)
+  uint32_t kbatch = 0;   // stage index: stage s lives in buffer s&1 and completes phase (s>>1)&1 of that buffer's mbarrier
+  for (uint32_t base = range.x; base < range.y; base += 256, buf ^= 1, ++kbatch) {
+    stage(buf ^ 1, id_next); issued = kbatch + 1;  // batch k+1 -> other buffer (free since the barrier that ended batch k-1)
     id_next = load_id(base + 512 + tid);           // ids of batch k+2
-    cp_async_wait<1>();                            // batch k has landed (this thread's copies) ...
-    __syncthreads();                               // ... and everyone else's
-    const float4 *s_a = s_rec[buf][0], *s_b = s_rec[buf][1], *s_c = s_rec[buf][2];
+    if (TMA) {
+      mbar_wait(&s_bar[buf], (kbatch >> 1) & 1u);  // all 256 arrivals + every announced byte of batch k have landed
+    } else {
+      cp_async_wait<1>();                          // batch k has landed (this thread's copies) ...
+      __syncthreads();                             // ... and everyone else's
+    }
+    const float4 *s_a = &s_rec[buf][0][0], *s_b = s_a + PS, *s_c = s_a + 2 * PS;
 
     const uint32_t cnt = min(256u, range.y - base);
     ++st_batches;
@@ -313,8 +367,8 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
       const uint32_t e = c0 + lane;
       bool hit = false;
       if (e < cnt) {
-        const float4 A = s_a[e];
-        const float hx = s_b[e].w, hy = s_c[e].w;
+        const float4 A = s_a[e * ES];
+        const float hx = s_b[e * ES].w, hy = s_c[e * ES].w;
         hit = (fabsf(A.x - bcx) <= hx + 3.5f) && (fabsf(A.y - bcy) <= hy + 1.5f);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, hit);
@@ -322,7 +376,7 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
         const uint32_t j = c0 + __ffs(mask) - 1;
         mask &= mask - 1;
         if (STATS) ++st_cand;
-        const float4 A = s_a[j], B = s_b[j];
+        const float4 A = s_a[j * ES], B = s_b[j * ES];
         const float dx = pxc - A.x, dy = A.y - pyc;  // pixel y grows down, NDC y up
         const float qa = fmaf(dy, A.w, dx * A.z), qb = fmaf(dy, B.y, dx * B.x);
         const bool inside = (fabsf(qa) <= 2.0f) && (fabsf(qb) <= 2.0f);  // quad corners at +-2 (:54-55)
@@ -332,7 +386,7 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
         const float alpha = __saturatef(exp_neg(power) * B.z);            // :82-86 (saturate: NaN -> 0, one instruction)
         if (inside && alpha >= 0.003921569f) {                            // discard below 1/255 (:103-104)
           if (STATS) ++st_blend;
-          const float4 C = s_c[j];
+          const float4 C = s_c[j * ES];
           const float om = 1.0f - d3;                                     // Blend OneMinusDstAlpha One (:11)
           float n0 = fmaf(C.x * alpha, om, d0), n1 = fmaf(C.y * alpha, om, d1), n2 = fmaf(C.z * alpha, om, d2),
                 n3 = fmaf(alpha, om, d3);
@@ -348,7 +402,12 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
     // frees this batch's buffer for the copies issued at the top of the next-but-one iteration.
     if (__syncthreads_and(d3 == 1.0f || !in_image)) break;
   }
-  cp_async_wait<0>();
+  if (TMA) {
+    // exactly one issued stage has not been waited for (the look-ahead one, or stage 0 of an empty list): drain it
+    mbar_wait(&s_bar[issued & 1u], (issued >> 1) & 1u);
+  } else {
+    cp_async_wait<0>();
+  }
   // this tile's cost for next frame's launch order: the slowest warp's work (evaluations dominate, culls and batches add)
   if (lane == 0) atomicMax(&s_cost, st_eval * 4 + st_batches * 16 + 1);
   __syncthreads();
@@ -381,6 +440,7 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
 }
 
 unsigned long long *g_raster_stats = nullptr;
+static constexpr int kRasterTmaDefault = 0;
 
 void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
                    uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s) {
@@ -398,13 +458,17 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const floa
   if (want < 0) { const char *e = getenv("GS_RASTER_STATS"); want = (e && e[0] == '1') ? 1 : 0; }
   if (want && !stats) { cudaMalloc(&stats, 64); g_raster_stats = stats; }
   if (stats) cudaMemsetAsync(stats, 0, 64, s);
+  // GS_RASTER_TMA=0/1: record staging by per-thread cp.async (16 B x 3) or by cp.async.bulk + mbarrier (48 B x 1)
+  static int tma = -1;
+  if (tma < 0) { const char *e = getenv("GS_RASTER_TMA"); tma = e ? (e[0] == '1') : kRasterTmaDefault; }
   const uint32_t bins = fc.binsX * fc.binsY;
   uint2 *ranges = reinterpret_cast<uint2 *>(bs.bin_ranges);
   k_bin_ranges<<<(bins + 7) / 8, 256, 0, s>>>(bs.tile_keys, bs.entry_count, bins, ranges);
 #define GS_LAUNCH_RASTER(ROP, FMT)                                                                                              \
   do {                                                                                                                         \
-    if (stats) k_raster<ROP, FMT, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
-    else k_raster<ROP, FMT, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
+    if (tma) k_raster<ROP, FMT, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
+    else if (stats) k_raster<ROP, FMT, true, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
+    else k_raster<ROP, FMT, false, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
   } while (0)
   if (rt_format == GS_PIX_RGBA16F) {
     if (rop) GS_LAUNCH_RASTER(true, GS_PIX_RGBA16F); else GS_LAUNCH_RASTER(false, GS_PIX_RGBA16F);
