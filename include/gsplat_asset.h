@@ -53,6 +53,7 @@ GSA_API int gsa_calc_sizes(uint32_t n, uint32_t pos_fmt, uint32_t scale_fmt, uin
  * then the five blobs (:705-1066).  `splats` is reordered and modified in place, exactly
  * like the reference's NativeArray.  Output buffers must have the sizes gsa_calc_sizes
  * reports; `chunks` may be NULL when the format set is fully float32.
+ * color_fmt 3 (BC7) and sh_fmt 4..8 (Cluster64k..4k) are the VeryLow / Low presets' formats (E/...:195-206).
  * bounds_out: 6 floats (min xyz, max xyz) or NULL. */
 GSA_API int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pos_fmt, uint32_t scale_fmt,
                              uint32_t color_fmt, uint32_t sh_fmt, void *pos, void *other, void *color,
@@ -69,6 +70,17 @@ GSA_API int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity
  * ply pair above.  Unlike PLY the records need no LinearizeData pass: the unpack already yields linear values. */
 GSA_API int64_t gsa_spz_vertex_count(const char *path);
 GSA_API int gsa_spz_read(const char *path, GsaInputSplat *out, uint32_t capacity);
+
+/* Mini-batch k-means with k-means++ seeding as the importer runs it for the Cluster4k..64k SH formats
+ * (E/Utils/KMeansClustering.cs:29-136, call site E/GaussianSplatAssetCreator.cs:476-518: dim 45, batch 2048,
+ * passes 0.3..1.2).  data: data_size x dim floats; out_means: k x dim; out_labels: data_size.  Deterministic. */
+GSA_API int gsa_kmeans(uint32_t dim, const float *data, uint32_t data_size, uint32_t batch_size, float passes_over_data,
+                       float *out_means, uint32_t k, int32_t *out_labels);
+
+/* One 4x4 block of float RGBA in [0,1] (raster order) -> 16 bytes of BC7 (mode 6).  Stands in for Unity's
+ * EditorUtility.CompressTexture (E/GaussianSplatAssetCreator.cs:901-912), which is closed source: lossy and not
+ * bit-identical to it, but any conformant BC7 decoder (the texture unit, gs_bc7.cuh) reads it. */
+GSA_API void gsa_bc7_encode_block(const float rgba[64], uint8_t out[16]);
 
 /* Individual pieces, exposed for tests. */
 GSA_API uint64_t gsa_morton_encode3(uint32_t x, uint32_t y, uint32_t z);       /* R/GaussianUtils.cs:81-95 */

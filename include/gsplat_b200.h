@@ -52,7 +52,8 @@ typedef enum GsVectorFormat { GS_VEC_FLOAT32 = 0, GS_VEC_NORM16 = 1, GS_VEC_NORM
 /* R/GaussianSplatAsset.cs:51-57 (ColorFormat) */
 typedef enum GsColorFormat { GS_COL_FLOAT32X4 = 0, GS_COL_FLOAT16X4 = 1, GS_COL_NORM8X4 = 2, GS_COL_BC7 = 3 } GsColorFormat;
 /* R/GaussianSplatAsset.cs:70-81 (SHFormat); values >= 4 are clustered palettes */
-typedef enum GsSHFormat { GS_SH_FLOAT32 = 0, GS_SH_FLOAT16 = 1, GS_SH_NORM11 = 2, GS_SH_NORM6 = 3, GS_SH_CLUSTER64K = 4 } GsSHFormat;
+typedef enum GsSHFormat { GS_SH_FLOAT32 = 0, GS_SH_FLOAT16 = 1, GS_SH_NORM11 = 2, GS_SH_NORM6 = 3, GS_SH_CLUSTER64K = 4,
+                          GS_SH_CLUSTER32K = 5, GS_SH_CLUSTER16K = 6, GS_SH_CLUSTER8K = 7, GS_SH_CLUSTER4K = 8 } GsSHFormat;
 
 /* The asset blobs exactly as GaussianSplatAsset exposes them
  * (R/GaussianSplatAsset.cs:219-237; uploaded by CreateResourcesForAsset,

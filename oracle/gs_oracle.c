@@ -138,6 +138,68 @@ static void load_vector(const void *buf, uint64_t addr, uint32_t fmt, float o[3]
   else dec_6_5_5(rd_u16(buf, addr), o);
 }
 
+/* ------------------------------------------------------------------ BC7 (ColorFormat.BC7, R/GaussianSplatAsset.cs:56,169)
+ * The reference samples a GraphicsFormat.RGBA_BC7_UNorm texture; the decode is done by the GPU's texture unit, i.e. by the
+ * published BC7/BPTC block format (D3D11 functional spec 19.5 / Khronos Data Format "BPTC"), not by code in /root/reference.
+ * Whole-block, spec-order restatement; pinned against an independent decoder (Pillow) by tests/golden/bc7_blocks.npz. */
+#include "bc7_tables.h"
+typedef struct Bc7Mode { uint8_t ns, pb, rb, isb, cb, ab, epb, spb, ib, ib2; } Bc7Mode;
+static const Bc7Mode kBc7Modes[8] = {
+    {3, 4, 0, 0, 4, 0, 1, 0, 3, 0}, {2, 6, 0, 0, 6, 0, 0, 1, 3, 0}, {3, 6, 0, 0, 5, 0, 0, 0, 2, 0}, {2, 6, 0, 0, 7, 0, 1, 0, 2, 0},
+    {1, 0, 2, 1, 5, 6, 0, 0, 2, 3}, {1, 0, 2, 0, 7, 8, 0, 0, 2, 2}, {1, 0, 0, 0, 7, 7, 1, 0, 4, 0}, {2, 6, 0, 0, 5, 5, 1, 0, 2, 0}};
+static const uint8_t kBc7W2[4] = {0, 21, 43, 64}, kBc7W3[8] = {0, 9, 18, 27, 37, 46, 55, 64},
+                     kBc7W4[16] = {0, 4, 9, 13, 17, 21, 26, 30, 34, 38, 43, 47, 51, 55, 60, 64};
+typedef struct Bc7Bits { const uint8_t *b; uint32_t pos; } Bc7Bits;
+static uint32_t bc7_get(Bc7Bits *r, uint32_t n) {
+  uint32_t v = 0;
+  for (uint32_t i = 0; i < n; ++i, ++r->pos) v |= (uint32_t)((r->b[r->pos >> 3] >> (r->pos & 7)) & 1u) << i;
+  return v;
+}
+void gso_bc7_decode_block(const uint8_t block[16], uint8_t out[64]) {
+  Bc7Bits r = {block, 0};
+  uint32_t mode = 0;
+  while (mode < 8 && !bc7_get(&r, 1)) ++mode;
+  if (mode == 8) { memset(out, 0, 64); return; } /* reserved: all channels 0 */
+  const Bc7Mode m = kBc7Modes[mode];
+  const uint32_t part = bc7_get(&r, m.pb), rot = bc7_get(&r, m.rb), isb = bc7_get(&r, m.isb);
+  uint32_t ep[6][4];
+  const uint32_t ne = m.ns * 2u;
+  for (uint32_t ch = 0; ch < 3; ++ch) for (uint32_t e = 0; e < ne; ++e) ep[e][ch] = bc7_get(&r, m.cb);
+  for (uint32_t e = 0; e < ne; ++e) ep[e][3] = m.ab ? bc7_get(&r, m.ab) : 0;
+  uint32_t cb = m.cb, ab = m.ab;
+  if (m.epb) {
+    for (uint32_t e = 0; e < ne; ++e) { uint32_t p = bc7_get(&r, 1); for (uint32_t ch = 0; ch < (m.ab ? 4u : 3u); ++ch) ep[e][ch] = (ep[e][ch] << 1) | p; }
+    cb += 1; if (m.ab) ab += 1;
+  }
+  if (m.spb) {
+    for (uint32_t s = 0; s < m.ns; ++s) { uint32_t p = bc7_get(&r, 1); for (uint32_t e = 2 * s; e < 2 * s + 2; ++e) for (uint32_t ch = 0; ch < 3; ++ch) ep[e][ch] = (ep[e][ch] << 1) | p; }
+    cb += 1;
+  }
+  for (uint32_t e = 0; e < ne; ++e) {
+    for (uint32_t ch = 0; ch < 3; ++ch) { uint32_t x = ep[e][ch] << (8 - cb); ep[e][ch] = x | (x >> cb); }
+    if (m.ab) { uint32_t x = ep[e][3] << (8 - ab); ep[e][3] = x | (x >> ab); } else ep[e][3] = 255;
+  }
+  uint32_t subset[16], anchor[3] = {0, 0, 0};
+  for (uint32_t i = 0; i < 16; ++i) subset[i] = m.ns == 1 ? 0u : m.ns == 2 ? ((kBc7Part2[part] >> i) & 1u) : ((kBc7Part3[part] >> (2 * i)) & 3u);
+  if (m.ns == 2) anchor[1] = kBc7Anchor2[part];
+  if (m.ns == 3) { anchor[1] = kBc7Anchor3a[part]; anchor[2] = kBc7Anchor3b[part]; }
+  uint32_t idx1[16], idx2[16];
+  for (uint32_t i = 0; i < 16; ++i) idx1[i] = bc7_get(&r, (i == anchor[subset[i]]) ? m.ib - 1u : m.ib);
+  for (uint32_t i = 0; i < 16; ++i) idx2[i] = m.ib2 ? bc7_get(&r, i == 0 ? m.ib2 - 1u : m.ib2) : 0;
+  for (uint32_t i = 0; i < 16; ++i) {
+    const uint32_t *e0 = ep[2 * subset[i]], *e1 = ep[2 * subset[i] + 1];
+    uint32_t ci = idx1[i], cbits = m.ib, ai = idx1[i], abits = m.ib;
+    if (m.ib2) { if (!isb) { ai = idx2[i]; abits = m.ib2; } else { ci = idx2[i]; cbits = m.ib2; } }
+    const uint32_t wc = cbits == 2 ? kBc7W2[ci] : cbits == 3 ? kBc7W3[ci] : kBc7W4[ci];
+    const uint32_t wa = abits == 2 ? kBc7W2[ai] : abits == 3 ? kBc7W3[ai] : kBc7W4[ai];
+    uint32_t px[4];
+    for (uint32_t ch = 0; ch < 3; ++ch) px[ch] = ((64 - wc) * e0[ch] + wc * e1[ch] + 32) >> 6;
+    px[3] = ((64 - wa) * e0[3] + wa * e1[3] + 32) >> 6;
+    if (rot) { uint32_t t = px[rot - 1]; px[rot - 1] = px[3]; px[3] = t; }
+    for (uint32_t ch = 0; ch < 4; ++ch) out[i * 4 + ch] = (uint8_t)px[ch];
+  }
+}
+
 typedef struct Chunk { /* SplatChunkInfo, :196-202 */
   uint32_t colR, colG, colB, colA;
   float posX[2], posY[2], posZ[2];
@@ -189,7 +251,13 @@ void gso_load_splat_data(const GsoAsset *a, uint32_t idx, GsoSplat *s) { /* Load
     uint64_t ti = gso_splat_index_to_pixel_index(idx, 0, 0);
     if (a->color_format == 0) { for (int k = 0; k < 4; ++k) col[k] = rd_f32(a->color, ti * 16 + 4 * k); }
     else if (a->color_format == 1) { for (int k = 0; k < 4; ++k) col[k] = gso_f16tof32(rd_u16(a->color, ti * 8 + 2 * k)); }
-    else { uint32_t e = rd_u32(a->color, ti * 4); for (int k = 0; k < 4; ++k) col[k] = (float)((e >> (8 * k)) & 255u) / 255.0f; }
+    else if (a->color_format == 2) { uint32_t e = rd_u32(a->color, ti * 4); for (int k = 0; k < 4; ++k) col[k] = (float)((e >> (8 * k)) & 255u) / 255.0f; }
+    else { /* BC7: 4x4 blocks of 16 bytes, row-major over the 2048-wide image; UNORM8 result / 255 */
+      uint32_t x, y; uint8_t px[64];
+      gso_splat_index_to_pixel_index(idx, &x, &y);
+      gso_bc7_decode_block((const uint8_t *)a->color + ((uint64_t)(y >> 2) * (2048u / 4u) + (x >> 2)) * 16u, px);
+      for (int k = 0; k < 4; ++k) col[k] = (float)px[((y & 3u) * 4u + (x & 3u)) * 4u + k] / 255.0f;
+    }
   }
   uint32_t shIndex = idx;
   if (shFmt > 3) shIndex = rd_u16(a->other, otherAddr + otherStride - 2);

@@ -81,6 +81,8 @@ GSO_API float gso_f16tof32(uint32_t h);
 GSO_API float gso_exp_neg(float x);              /* deterministic exp for the pixel shader */
 GSO_API uint32_t gso_float_to_sortable_uint(float f);  /* S/SplatUtilities.compute:52-57 */
 GSO_API float gso_inv_square_centered01(float x);      /* S/GaussianSplatting.hlsl:5-11 */
+/* BC7 (BPTC) block -> 16 RGBA8 pixels in raster order; what the texture unit does for ColorFormat.BC7 (R/GaussianSplatAsset.cs:169) */
+GSO_API void gso_bc7_decode_block(const uint8_t block[16], uint8_t out_rgba[64]);
 GSO_API uint32_t gso_splat_index_to_pixel_index(uint32_t idx, uint32_t *x, uint32_t *y); /* :183-194 */
 
 /* ---- decode (LoadSplatData / LoadSplatPos, S/GaussianSplatting.hlsl:394-421,428-608) ---- */

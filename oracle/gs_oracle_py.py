@@ -65,12 +65,23 @@ def lib():
         L.gso_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
         L.gso_composite.restype, L.gso_composite.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
         L.gso_max_threads.restype, L.gso_max_threads.argtypes = C.c_int, []
+        L.gso_bc7_decode_block.restype, L.gso_bc7_decode_block.argtypes = None, [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
 
 def max_threads() -> int:
     return int(lib().gso_max_threads())
+
+
+def bc7_decode_blocks(blocks: np.ndarray) -> np.ndarray:
+    """(n,16) uint8 BC7 blocks -> (n,16,4) uint8 RGBA pixels, raster order inside each block."""
+    blocks = np.ascontiguousarray(blocks, np.uint8).reshape(-1, 16)
+    out = np.zeros((blocks.shape[0], 16, 4), np.uint8)
+    L = lib()
+    for i in range(blocks.shape[0]):
+        L.gso_bc7_decode_block(blocks[i].ctypes.data, out[i].ctypes.data)
+    return out
 
 
 def asset_struct(asset) -> GsoAsset:

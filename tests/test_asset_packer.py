@@ -23,8 +23,12 @@ def test_sizes_match_the_reference_formulas(g):
     total = sz.pos_bytes + sz.other_bytes + sz.sh_bytes + sz.color_bytes + sz.chunk_bytes
     assert abs(total / 2**20 - 282.3) < 0.1
     assert N.asset_lib().gsa_calc_sizes(n, 0, 0, 0, 0, C.byref(sz)) == 0 and sz.chunk_bytes == 0   # lossless: no chunks
-    assert N.asset_lib().gsa_calc_sizes(n, 2, 2, 3, 3, C.byref(sz)) != 0    # BC7: out of scope
-    assert N.asset_lib().gsa_calc_sizes(n, 2, 2, 2, 4, C.byref(sz)) != 0    # clustered SH: out of scope
+    # VeryLow preset (E/GaussianSplatAssetCreator.cs:195-200): BC7 = 1 byte per texel, palette of 4096 x 96 B, u16 index per splat
+    assert N.asset_lib().gsa_calc_sizes(n, 2, 3, 3, 8, C.byref(sz)) == 0
+    assert sz.color_bytes == 2048 * 3008 and sz.sh_bytes == 4096 * 96 and sz.other_bytes == (n * 8 + 7) // 8 * 8
+    assert N.asset_lib().gsa_calc_sizes(n, 2, 2, 2, 4, C.byref(sz)) == 0 and sz.sh_bytes == 65536 * 96 and sz.other_bytes == (n * 10 + 7) // 8 * 8
+    assert N.asset_lib().gsa_calc_sizes(4096, 2, 3, 3, 8, C.byref(sz)) != 0   # palette not smaller than the data
+    assert N.asset_lib().gsa_calc_sizes(n, 2, 2, 4, 3, C.byref(sz)) != 0 and N.asset_lib().gsa_calc_sizes(n, 2, 2, 2, 9, C.byref(sz)) != 0
 
 
 def test_generation_is_deterministic(g):

@@ -64,6 +64,26 @@ def test_clustered_scene(g, O, ctx, quality, n, w, h):
     _assert_frame(got, ref)
 
 
+@pytest.mark.parametrize("quality,n,w,h", [("VeryLow", 20000, 333, 211), ("Low", 17000, 320, 180)])
+def test_low_presets_bc7_and_clustered_sh(g, O, ctx, quality, n, w, h):
+    """BC7 colour (single-texel decode in k_calc_view) and Cluster4k/16k SH palettes (u16 index in `other`)."""
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, n, 0x5EED0031, quality)
+    got, ref = _frame_pair(g, O, ctx, asset, camera(g, w, h))
+    _assert_frame(got, ref)
+
+
+def test_bc7_all_modes_through_the_view_kernel(g, O, ctx):
+    """A VeryLow asset whose colour blob is replaced by the golden random blocks of all eight BC7 modes."""
+    d = np.load(__import__("pathlib").Path(__file__).with_name("golden") / "bc7_blocks.npz")
+    n = 20000
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, n, 0x5EED0032, "VeryLow")
+    blocks = d["blocks"].reshape(-1)
+    reps = -(-asset.colorData.nbytes // blocks.size)
+    asset.colorData = np.ascontiguousarray(np.tile(blocks, reps)[:asset.colorData.nbytes])
+    got, ref = _frame_pair(g, O, ctx, asset, camera(g, 256, 192))
+    _assert_frame(got, ref)
+
+
 def test_fp32_blend_mode(g, O, ctx):
     asset = g.synthetic_asset(g.SCENE_CLUSTERED, 40000, 0x5EED0002, "Medium")
     got, ref = _frame_pair(g, O, ctx, asset, camera(g, 320, 240), blend=1)

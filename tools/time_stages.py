@@ -9,7 +9,8 @@ import numpy as np
 import bench
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else bench.N_SPLATS
-g, asset, cam = bench.make_scene(n)
+quality = sys.argv[2] if len(sys.argv) > 2 else "Medium"
+g, asset, cam = bench.make_scene(n, quality)
 ctx = g.GaussianSplatContext(0)
 r = g.GaussianSplatRenderer(asset, ctx)
 import torch

@@ -118,6 +118,8 @@ ASSET_SYMBOLS = {
     "gsa_splat_index_to_texture_index": (C.c_uint32, [C.c_uint32]),
     "gsa_pack_smallest3": (None, [C.c_void_p, C.c_void_p]),
     "gsa_f32tof16": (C.c_uint32, [C.c_float]),
+    "gsa_kmeans": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "gsa_bc7_encode_block": (None, [C.c_void_p, C.c_void_p]),
 }
 
 

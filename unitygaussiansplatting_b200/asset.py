@@ -42,8 +42,10 @@ class SHFormat(IntEnum):  # R/GaussianSplatAsset.cs:70-81
     Cluster4k = 8
 
 
-# E/GaussianSplatAssetCreator.cs:195-224 -- presets the native path can decode (no BC7 / clustered SH)
+# E/GaussianSplatAssetCreator.cs:195-224 -- the importer's five presets
 QUALITY = {
+    "VeryLow": (VectorFormat.Norm11, VectorFormat.Norm6, ColorFormat.BC7, SHFormat.Cluster4k),
+    "Low": (VectorFormat.Norm11, VectorFormat.Norm6, ColorFormat.Norm8x4, SHFormat.Cluster16k),
     "Medium": (VectorFormat.Norm11, VectorFormat.Norm11, ColorFormat.Norm8x4, SHFormat.Norm6),
     "High": (VectorFormat.Norm16, VectorFormat.Norm16, ColorFormat.Float16x4, SHFormat.Norm11),
     "VeryHigh": (VectorFormat.Float32, VectorFormat.Float32, ColorFormat.Float32x4, SHFormat.Float32),
@@ -134,7 +136,7 @@ def create_asset(splats: np.ndarray, quality: str = "Medium", formats=None) -> G
     lib = N.asset_lib()
     sz = N.GsaSizes()
     if lib.gsa_calc_sizes(n, int(pf), int(sf), int(cf), int(shf), C.byref(sz)) != 0:
-        raise ValueError("unsupported format combination (BC7 / clustered SH are out of scope)")
+        raise ValueError("unsupported format combination (clustered SH needs more splats than palette entries)")
     pos = np.zeros(sz.pos_bytes, np.uint8)
     other = np.zeros(sz.other_bytes, np.uint8)
     color = np.zeros(sz.color_bytes, np.uint8)

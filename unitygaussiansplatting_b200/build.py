@@ -24,7 +24,7 @@ NATIVE_LIB = PKG / "libgsplat_b200.so"
 ASSET_LIB = PKG / "libgsplat_asset.so"
 
 CU_SOURCES = ["gs_api.cu", "gs_view.cu", "gs_sort.cu", "gs_raster.cu"]
-CU_HEADERS = ["gs_common.cuh", "gs_kernels.cuh", "../../include/gsplat_b200.h"]
+CU_HEADERS = ["gs_common.cuh", "gs_kernels.cuh", "gs_bc7.cuh", "bc7_tables.h", "../../include/gsplat_b200.h"]
 
 
 def _host_cxx() -> str:
@@ -78,10 +78,11 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build_asset(force: bool = False) -> Path:
-    src = CSRC / "asset_creator.cpp"
-    if force or _stale(ASSET_LIB, [src, ROOT / "include" / "gsplat_asset.h"]):
-        _run([_host_cxx(), "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",
-              "-o", str(ASSET_LIB), str(src), "-lz"])
+    srcs = [CSRC / "asset_creator.cpp", CSRC / "asset_cluster_bc7.cpp"]
+    if force or _stale(ASSET_LIB, [*srcs, ROOT / "include" / "gsplat_asset.h"]):
+        # -mavx2: the k-means distance loops evaluate 16 candidate means side by side (no FMA: -ffp-contract=off)
+        _run([_host_cxx(), "-O3", "-mavx2", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",
+              "-o", str(ASSET_LIB), *map(str, srcs), "-lz"])
     return ASSET_LIB
 
 

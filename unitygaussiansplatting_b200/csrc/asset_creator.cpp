@@ -156,8 +156,11 @@ inline uint32_t vector_size(uint32_t fmt) {  // R/GaussianSplatAsset.cs:39-49
 inline uint32_t color_size(uint32_t fmt) {  // R/GaussianSplatAsset.cs:58-68
   switch (fmt) { case 0: return 16; case 1: return 8; case 2: return 4; case 3: return 1; default: return 0; }
 }
-inline uint32_t sh_stride(uint32_t fmt) {  // R/GaussianSplatAsset.cs:83-101
-  switch (fmt) { case 0: return 192; case 1: return 96; case 2: return 60; case 3: return 32; default: return 0; }
+inline uint32_t sh_stride(uint32_t fmt) {  // R/GaussianSplatAsset.cs:83-101 (clustered formats: SHTableItemFloat16 palette entries)
+  switch (fmt) { case 0: return 192; case 1: return 96; case 2: return 60; case 3: return 32; default: return fmt <= 8 ? 96 : 0; }
+}
+inline uint32_t sh_count(uint32_t fmt, uint32_t n) {  // GetSHCount, R/GaussianSplatAsset.cs:135-150
+  return fmt <= 3 ? n : (65536u >> (fmt - 4));
 }
 inline uint64_t next_multiple(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 
@@ -274,16 +277,19 @@ int gsa_generate(uint32_t kind, uint32_t n, uint32_t seed, GsaInputSplat *out) {
 }
 
 int gsa_calc_sizes(uint32_t n, uint32_t pf, uint32_t sf, uint32_t cf, uint32_t shf, GsaSizes *out) {
-  if (!out || pf > 3 || sf > 3 || cf > 2 || shf > 3) return -1;  // BC7 / clustered SH: unsupported
+  if (!out || pf > 3 || sf > 3 || cf > 3 || shf > 8) return -1;
+  // the reference skips clustering when the palette would not be smaller than the data (E/...:480-482) and then writes an
+  // asset its own shader mis-reads (no index in `other`, empty SH blob); refuse that combination instead
+  if (shf > 3 && n <= sh_count(shf, n)) return -1;
   uint32_t width = kTexWidth;
   uint32_t height = std::max<uint32_t>(1, (n + width - 1) / width);
   height = (height + 15) / 16 * 16;  // R/GaussianSplatAsset.cs:152-160
   out->tex_width = width;
   out->tex_height = height;
   out->pos_bytes = next_multiple((uint64_t)n * vector_size(pf), 8);          // E/...:815
-  out->other_bytes = next_multiple((uint64_t)n * (4 + vector_size(sf)), 8);  // E/...:842
+  out->other_bytes = next_multiple((uint64_t)n * (4 + vector_size(sf) + (shf > 3 ? 2 : 0)), 8);  // E/...:837-842
   out->color_bytes = (uint64_t)width * height * color_size(cf);
-  out->sh_bytes = (uint64_t)n * sh_stride(shf);
+  out->sh_bytes = (uint64_t)sh_count(shf, n) * sh_stride(shf);  // clustered: the palette only (E/...:1048-1051)
   out->chunk_bytes = uses_chunks(pf, sf, cf, shf) ? (uint64_t)((n + kChunkSize - 1) / kChunkSize) * 64 : 0;
   return 0;
 }
@@ -329,6 +335,25 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
     std::vector<GsaInputSplat> copy(splats, splats + n);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) splats[i] = copy[order[i].second];
+  }
+
+  // ---- SH palette (E/...:284-291, 476-518): k-means over the raw (not yet chunk-normalised) SH vectors ----
+  std::vector<int32_t> sh_labels;
+  if (shf > 3) {
+    const uint32_t k = sh_count(shf, n);
+    static const float kPasses[5] = {0.3f, 0.4f, 0.5f, 0.8f, 1.2f};  // Cluster64k..4k, E/...:487-495
+    std::vector<float> sh_data((size_t)n * 45), means((size_t)k * 45);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) std::memcpy(&sh_data[(size_t)i * 45], splats[i].sh, 180);  // GatherSHs :431-440
+    sh_labels.resize(n);
+    if (gsa_kmeans(45, sh_data.data(), n, 2048, kPasses[shf - 4], means.data(), k, sh_labels.data()) != 0) return -4;
+    uint8_t *tab = (uint8_t *)sh_out;  // ConvertSHClustersJob :443-468: 15 x half3 + one padding half3 = 96 bytes
+    std::memset(tab, 0, (size_t)k * 96);
+    for (uint32_t j = 0; j < k; ++j) {
+      uint16_t h[45];
+      for (int c = 0; c < 45; ++c) h[c] = (uint16_t)unity_f32tof16(means[(size_t)j * 45 + c]);
+      std::memcpy(tab + (size_t)j * 96, h, 90);
+    }
   }
 
   // ---- chunk min/max + normalise (E/...:520-639) ----
@@ -395,9 +420,12 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
   std::memset(pos_out, 0, sz.pos_bytes);
   std::memset(other_out, 0, sz.other_bytes);
   std::memset(color_out, 0, sz.color_bytes);
-  std::memset(sh_out, 0, sz.sh_bytes);
-  const uint32_t pstride = vector_size(pf), ostride = 4 + vector_size(sf), cstride = color_size(cf),
+  if (shf <= 3) std::memset(sh_out, 0, sz.sh_bytes);
+  const uint32_t pstride = vector_size(pf), ostride = 4 + vector_size(sf) + (shf > 3 ? 2 : 0), cstride = color_size(cf),
                  hstride = sh_stride(shf);
+  // BC7 is encoded from the float image, 4x4 texels at a time (E/...:887-912)
+  std::vector<float> image;
+  if (cf == 3) image.assign((size_t)sz.tex_width * sz.tex_height * 4, 0.0f);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)n; ++i) {
     const GsaInputSplat &s = splats[i];
@@ -407,10 +435,14 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
     uint32_t rq = enc_quat10(s.rot);
     std::memcpy(o, &rq, 4);
     emit_vector(s.scale, o + 4, sf);
+    if (shf > 3) { uint16_t l = (uint16_t)sh_labels[i]; std::memcpy(o + ostride - 2, &l, 2); }  // E/...:801-803
     // colour texel, Morton-swizzled (E/...:873-885, 661-703)
-    uint8_t *cdst = (uint8_t *)color_out + (uint64_t)splat_index_to_texture_index((uint32_t)i) * cstride;
+    const uint64_t texel = splat_index_to_texture_index((uint32_t)i);
+    uint8_t *cdst = (uint8_t *)color_out + texel * cstride;
     float pix[4] = {s.dc0[0], s.dc0[1], s.dc0[2], s.opacity};
-    if (cf == 0) {
+    if (cf == 3) {
+      std::memcpy(&image[texel * 4], pix, 16);
+    } else if (cf == 0) {
       std::memcpy(cdst, pix, 16);
     } else if (cf == 1) {
       uint16_t h[4];
@@ -423,6 +455,7 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
       std::memcpy(cdst, &enc, 4);
     }
     // SH table item (E/...:934-1037)
+    if (shf > 3) continue;  // palette already written
     uint8_t *h = (uint8_t *)sh_out + (uint64_t)i * hstride;
     if (shf == 0) {
       std::memcpy(h, s.sh, 180);  // 12 bytes of padding stay zero
@@ -439,6 +472,17 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
       for (int j = 0; j < 15; ++j) t[j] = enc_norm565(&s.sh[j * 3]);
       t[15] = 0;
       std::memcpy(h, t, 32);
+    }
+  }
+  if (cf == 3) {
+    const uint32_t bw = sz.tex_width / 4, bh = sz.tex_height / 4;
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < (int64_t)bw * bh; ++b) {
+      const uint32_t bx = (uint32_t)(b % bw), by = (uint32_t)(b / bw);
+      float blk[64];
+      for (int y = 0; y < 4; ++y)
+        std::memcpy(&blk[y * 16], &image[((size_t)(by * 4 + y) * sz.tex_width + bx * 4) * 4], 64);
+      gsa_bc7_encode_block(blk, (uint8_t *)color_out + (size_t)b * 16);
     }
   }
   return 0;

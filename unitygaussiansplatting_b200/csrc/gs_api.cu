@@ -428,32 +428,40 @@ int gs_asset_upload(GsContext *ctx, const GsAssetDesc *d, GsAsset **out) {
   // HasValidAsset, R/GaussianSplatRenderer.cs:361-368
   if (d->splat_count == 0 || !d->pos || !d->other || !d->sh || !d->color) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "asset has no splats or a null blob");
   if (d->pos_format > 3 || d->scale_format > 3) return fail(ctx, GS_ERR_UNSUPPORTED_FORMAT, "unknown vector format");
-  if (d->color_format > GS_COL_NORM8X4) return fail(ctx, GS_ERR_UNSUPPORTED_FORMAT, "BC7 colour is not supported by the native path");
-  if (d->sh_format > GS_SH_NORM6) return fail(ctx, GS_ERR_UNSUPPORTED_FORMAT, "clustered SH palettes are not supported by the native path");
+  if (d->color_format > GS_COL_BC7) return fail(ctx, GS_ERR_UNSUPPORTED_FORMAT, "unknown colour format");
+  if (d->sh_format > GS_SH_CLUSTER4K) return fail(ctx, GS_ERR_UNSUPPORTED_FORMAT, "unknown SH format");
   const uint64_t n = d->splat_count;
-  const uint32_t colsz = d->color_format == 0 ? 16u : d->color_format == 1 ? 8u : 4u;
-  const uint32_t shst = d->sh_format == 0 ? 192u : d->sh_format == 1 ? 96u : d->sh_format == 2 ? 60u : 32u;
+  // bytes per texel: Float32x4 16, Float16x4 8, Norm8x4 4, BC7 1 (16-byte 4x4 blocks), R/GaussianSplatAsset.cs:58-68
+  const uint32_t colsz = d->color_format == 0 ? 16u : d->color_format == 1 ? 8u : d->color_format == 2 ? 4u : 1u;
+  // clustered SH (R/GaussianSplatAsset.cs:135-150,187-198): the blob is a palette of 64k..4k Float16 entries and every
+  // splat carries a u16 palette index at the end of its `other` record (S/GaussianSplatting.hlsl:447-448,467-470)
+  const bool clustered = d->sh_format > GS_SH_NORM6;
+  const uint64_t sh_items = clustered ? (uint64_t)(65536u >> (d->sh_format - GS_SH_CLUSTER64K)) : n;
+  const uint32_t shst = d->sh_format == 0 ? 192u : (d->sh_format == 1 || clustered) ? 96u : d->sh_format == 2 ? 60u : 32u;
   uint32_t th = (uint32_t)((n + kTexWidth - 1) / kTexWidth);
   th = (th + 15) / 16 * 16;
-  if (d->pos_bytes < n * vec_stride(d->pos_format) || d->other_bytes < n * (4 + vec_stride(d->scale_format)) ||
-      d->sh_bytes < n * shst || d->color_bytes < (uint64_t)kTexWidth * th * colsz)
+  if (d->pos_bytes < n * vec_stride(d->pos_format) || d->other_bytes < n * (4 + vec_stride(d->scale_format) + (clustered ? 2u : 0u)) ||
+      d->sh_bytes < sh_items * shst || d->color_bytes < (uint64_t)kTexWidth * th * colsz)
     return fail(ctx, GS_ERR_INVALID_ARGUMENT, "asset blob smaller than its format requires");
   const uint32_t chunk_count = (d->chunks && d->chunk_bytes) ? (uint32_t)(d->chunk_bytes / 64) : 0;
   GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   GsAsset *as = new (std::nothrow) GsAsset();
   if (!as) return fail(ctx, GS_ERR_OUT_OF_MEMORY, "host allocation failed");
   as->ctx = ctx;
-  auto up = [&](void **dst, const void *src, uint64_t bytes) -> cudaError_t {
+  auto up = [&](void **dst, const void *src, uint64_t bytes, uint64_t min_bytes = 0) -> cudaError_t {
     // +16 bytes of slack: the widest vector load of the last splat may read past a tightly sized blob
-    cudaError_t e = cudaMalloc(dst, bytes + 16);
+    const uint64_t alloc = (bytes > min_bytes ? bytes : min_bytes) + 16;
+    cudaError_t e = cudaMalloc(dst, alloc);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync((uint8_t *)*dst + bytes, 0, 16, ctx->stream);
+    e = cudaMemsetAsync((uint8_t *)*dst + bytes, 0, alloc - bytes, ctx->stream);
     if (e != cudaSuccess) return e;
     return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
   };
+  // a u16 palette index can name any of 65536 entries whatever the palette's nominal size: back all of them (zeros)
+  const uint64_t sh_min = clustered ? 65536ull * 96ull : 0ull;
   cudaError_t e = cudaSuccess;
   if ((e = up(&as->d_pos, d->pos, d->pos_bytes)) != cudaSuccess || (e = up(&as->d_other, d->other, d->other_bytes)) != cudaSuccess ||
-      (e = up(&as->d_sh, d->sh, d->sh_bytes)) != cudaSuccess || (e = up(&as->d_color, d->color, d->color_bytes)) != cudaSuccess ||
+      (e = up(&as->d_sh, d->sh, d->sh_bytes, sh_min)) != cudaSuccess || (e = up(&as->d_color, d->color, d->color_bytes)) != cudaSuccess ||
       (chunk_count && (e = up(&as->d_chunks, d->chunks, (uint64_t)chunk_count * 64)) != cudaSuccess) ||
       (e = cudaMalloc(&as->order, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->keys, n * 4)) != cudaSuccess ||
       (e = cudaMalloc(&as->key_table, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->draw, n * 48)) != cudaSuccess ||

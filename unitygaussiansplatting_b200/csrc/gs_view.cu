@@ -13,6 +13,7 @@
 //     8-bit digit histograms on the way; the gather through last frame's order is folded into
 //     pass 0 of the radix sort, so neither a histogram read nor a gathered key array exists.
 #include "gs_kernels.cuh"
+#include "gs_bc7.cuh"
 
 namespace gs {
 
@@ -177,6 +178,8 @@ struct ShRaw<1> {  // Float16: 45 halfs + pad = 96 B
   __device__ __forceinline__ float3 get(int j) const { return make_float3(h(j * 3), h(j * 3 + 1), h(j * 3 + 2)); }
 };
 template <>
+struct ShRaw<4> : ShRaw<1> {};  // Cluster4k..64k: a Float16 palette entry (SHTableItemFloat16), picked by a per-splat u16 index
+template <>
 struct ShRaw<0> {  // Float32: 45 floats + pad = 192 B
   uint32_t w[48];
   __device__ __forceinline__ void load(const uint8_t *p) {
@@ -204,8 +207,14 @@ __device__ __forceinline__ float3 neg(float3 a) { return make_float3(-a.x, -a.y,
 // colour half (SH fetch + ShadeSH, 2/3 of the bytes, ~half of the arithmetic) is dead code too.  gs_calc_view (the
 // stand-alone entry point) always runs the full kernel, so _SplatViewData parity is checked on that one.
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// where texel `ti` of the 2048-wide colour image lives (BC7: its 16-byte 4x4 block, blocks row-major)
+template <bool BC7>
+__device__ __forceinline__ const uint8_t *color_texel_ptr(const AssetView &a, uint32_t ti) {
+  if (BC7) return a.color + ((uint64_t)((ti / kTexWidth) >> 2) * (kTexWidth / 4) + ((ti & (kTexWidth - 1)) >> 2)) * 16u;
+  return a.color + (uint64_t)ti * (a.colFmt == 0 ? 16u : a.colFmt == 1 ? 8u : 4u);
+}
 
-template <int SHFMT, bool CULL>
+template <int SHFMT, bool CULL, bool BC7>
 __global__ void __launch_bounds__(256)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
             uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out, Partition part) {
@@ -219,10 +228,10 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
   // memory latency, not two (a CTA with nothing to draw was 2 dependent round trips long)
   if (idx < a.n) {
     prefetch_l1(a.pos + (uint64_t)idx * vec_stride(a.posFmt));
-    prefetch_l1(a.other + (uint64_t)idx * (4 + vec_stride(a.scaleFmt)));
+    prefetch_l1(a.other + (uint64_t)idx * (4 + vec_stride(a.scaleFmt) + (SHFMT == 4 ? 2u : 0u)));
     if (!CULL) {
-      prefetch_l1(a.color + (uint64_t)splat_index_to_texel(idx) * (a.colFmt == 0 ? 16u : a.colFmt == 1 ? 8u : 4u));
-      if (fc.shOrder >= 1) prefetch_l1(a.sh + (uint64_t)idx * (SHFMT == 0 ? 192u : SHFMT == 1 ? 96u : SHFMT == 2 ? 60u : 32u));
+      prefetch_l1(color_texel_ptr<BC7>(a, splat_index_to_texel(idx)));
+      if (fc.shOrder >= 1 && SHFMT != 4) prefetch_l1(a.sh + (uint64_t)idx * (SHFMT == 0 ? 192u : SHFMT == 1 ? 96u : SHFMT == 2 ? 60u : 32u));
     }
   }
   __syncthreads();
@@ -277,16 +286,16 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
 
   if (idx < a.n) {
     // ---- LoadSplatData, S/GaussianSplatting.hlsl:428-608 ----
-    const uint32_t otherStride = 4 + vec_stride(a.scaleFmt);
+    const uint32_t otherStride = 4 + vec_stride(a.scaleFmt) + (SHFMT == 4 ? 2u : 0u);  // + u16 SH index when clustered, :447-448
     const uint64_t otherAddr = (uint64_t)idx * otherStride;
     float3 pos = load_vector(a.pos, (uint64_t)idx * vec_stride(a.posFmt), a.posFmt);
     uint32_t rq;
     float3 scale;
-    if (a.scaleFmt == 2) {  // 8-byte record: one aligned 64-bit load
+    if (SHFMT != 4 && a.scaleFmt == 2) {  // 8-byte record: one aligned 64-bit load
       uint2 o = __ldg(reinterpret_cast<const uint2 *>(a.other + otherAddr));
       rq = o.x;
       scale = dec_11_10_11(o.y);
-    } else if (a.scaleFmt == 0) {  // 16-byte record
+    } else if (SHFMT != 4 && a.scaleFmt == 0) {  // 16-byte record
       uint4 o = __ldg(reinterpret_cast<const uint4 *>(a.other + otherAddr));
       rq = o.x;
       scale = make_float3(__uint_as_float(o.y), __uint_as_float(o.z), __uint_as_float(o.w));
@@ -318,16 +327,25 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
         uint2 e = __ldg(reinterpret_cast<const uint2 *>(a.color) + ti);
         col = make_float4(f16lo(e.x), f16hi(e.x), f16lo(e.y), f16hi(e.y));
       } else {
-        uint32_t e = __ldg(reinterpret_cast<const uint32_t *>(a.color) + ti);
+        uint32_t e;
+        if (!BC7) {
+          e = __ldg(reinterpret_cast<const uint32_t *>(a.color) + ti);
+        } else {  // BC7: the texel's 4x4 block (16 B), then the one texel this splat owns (gs_bc7.cuh)
+          const uint32_t x = ti & (kTexWidth - 1), y = ti / kTexWidth;
+          const uint4 b = __ldg(reinterpret_cast<const uint4 *>(color_texel_ptr<true>(a, ti)));
+          e = bc7::decode_texel(b.x, b.y, b.z, b.w, (y & 3u) * 4u + (x & 3u));
+        }
         col = make_float4(__fdiv_rn((float)(e & 255u), 255.0f), __fdiv_rn((float)((e >> 8) & 255u), 255.0f),
                           __fdiv_rn((float)((e >> 16) & 255u), 255.0f), __fdiv_rn((float)(e >> 24), 255.0f));
       }
     };
     ShRaw<SHFMT> shr;
-    constexpr uint32_t shStride = SHFMT == 0 ? 192u : SHFMT == 1 ? 96u : SHFMT == 2 ? 60u : 32u;
+    constexpr uint32_t shStride = SHFMT == 0 ? 192u : (SHFMT == 1 || SHFMT == 4) ? 96u : SHFMT == 2 ? 60u : 32u;
+    // shIndex, :467-470: the splat's own slot, or its palette entry
+    const uint32_t shIdx = SHFMT == 4 ? ld_u16(a.other + otherAddr + otherStride - 2) : idx;
     if (!CULL) {
       load_color();
-      if (fc.shOrder >= 1) shr.load(a.sh + (uint64_t)idx * shStride);
+      if (fc.shOrder >= 1) shr.load(a.sh + (uint64_t)shIdx * shStride);
     }
 
     float3 shMin = make_float3(0.f, 0.f, 0.f), shMax = make_float3(1.f, 1.f, 1.f);
@@ -358,7 +376,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
       }
     };
     if (!CULL) finish_color();
-    const bool shLerp = chunked && SHFMT != 0;  // shFormat > FLOAT32 && <= NORM6, :585
+    const bool shLerp = chunked && SHFMT != 0 && SHFMT != 4;  // shFormat > FLOAT32 && <= NORM6, :585
     auto SH = [&](int j) -> float3 {
       float3 v = shr.get(j - 1);
       if (shLerp) { v.x = lerpf(shMin.x, shMax.x, v.x); v.y = lerpf(shMin.y, shMax.y, v.y); v.z = lerpf(shMin.z, shMax.z, v.z); }
@@ -456,7 +474,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
           finish_color();
           // alpha = sat(exp_neg(..) * half(min(opacity*scale, 65000))) stays below 1/255 when the half is below 0.00392
           drawable = __half2float(__float2half_rn(fminf(col.w * fc.opacityScale, 65000.0f))) >= 0.00392f;
-          if (drawable && fc.shOrder >= 1) shr.load(a.sh + (uint64_t)idx * shStride);
+          if (drawable && fc.shOrder >= 1) shr.load(a.sh + (uint64_t)shIdx * shStride);
         }
       }
       if (drawable) {
@@ -539,12 +557,20 @@ template <bool CULL>
 static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
                                uint32_t *rect, float4 *draw, const Partition &part, cudaStream_t s) {
   const uint32_t grid = (a.n + 255) / 256;
+  // BC7 colour (VeryLow preset) is a separate instantiation: the block decode must not cost the other formats registers
+#define GS_VIEW(SH)                                                                                                        \
+  do {                                                                                                                    \
+    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part);  \
+    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part);               \
+  } while (0)
   switch (a.shFmt) {
-    case 0: k_calc_view<0, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part); break;
-    case 1: k_calc_view<1, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part); break;
-    case 2: k_calc_view<2, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part); break;
-    default: k_calc_view<3, CULL><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part); break;
+    case 0: GS_VIEW(0); break;
+    case 1: GS_VIEW(1); break;
+    case 2: GS_VIEW(2); break;
+    case 3: GS_VIEW(3); break;
+    default: GS_VIEW(4); break;  // Cluster64k..4k
   }
+#undef GS_VIEW
 }
 
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
