@@ -66,6 +66,11 @@ GSA_API int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pos_fmt
 GSA_API int64_t gsa_ply_vertex_count(const char *path);
 GSA_API int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity);
 
+/* .ply output (E/GaussianSplatRendererEditor.cs:394-445, ExportPlyFile): `records` = n x 62 raw attribute values (what
+ * gs_export_splats returns); records with a deleted bit (may be NULL) or a non-zero normal (cut marker) are dropped.
+ * Returns the number of vertices written, < 0 on I/O error. */
+GSA_API int64_t gsa_ply_write(const char *path, const float *records, uint32_t n, const uint32_t *deleted_bits);
+
 /* Niantic/Scaniverse .spz input (gzip stream, version 2; E/Utils/SPZFileReader.cs:20-195): same contract as the
  * ply pair above.  Unlike PLY the records need no LinearizeData pass: the unpack already yields linear values. */
 GSA_API int64_t gsa_spz_vertex_count(const char *path);

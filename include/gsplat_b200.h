@@ -42,7 +42,7 @@ typedef enum GsStatus {
   GS_ERR_INVALID_ARGUMENT = -1,
   GS_ERR_CUDA = -2,
   GS_ERR_OUT_OF_MEMORY = -3,
-  GS_ERR_UNSUPPORTED_FORMAT = -4, /* BC7 colour, clustered SH palettes */
+  GS_ERR_UNSUPPORTED_FORMAT = -4, /* a format enum outside R/GaussianSplatAsset.cs:31-81 */
   GS_ERR_NOT_READY = -5,          /* e.g. gs_render before gs_calc_view */
   GS_ERR_NO_DEVICE = -6
 } GsStatus;
@@ -203,6 +203,16 @@ GS_API int gs_unshuffle_bands(GsContext *ctx, const void *gathered, uint32_t par
 GS_API int gs_sort_pairs_device(GsContext *ctx, uint32_t *d_keys, uint32_t *d_payload, uint32_t count);
 /* Same through HOST buffers (copies in, sorts, copies out, blocks). */
 GS_API int gs_sort_pairs_host(GsContext *ctx, uint32_t *keys, uint32_t *payload, uint32_t count);
+
+/* ---- export (EditExportData, R/GaussianSplatRenderer.cs:936-958 -> CSExportData, S/SplatUtilities.compute:616-669) ---- */
+/* Decodes every splat of the uploaded asset back to the INRIA .ply attribute record: n x 62 floats in HOST memory `dst`
+ * (pos, nor, f_dc, f_rest channel-major, opacity as logit, log scale, rot wxyz -- the InputSplatData layout,
+ * E/Utils/GaussianFileReader.cs:17-26).  nor = (1,1,1) marks a splat the cutouts remove (`cutouts` as in GsFrameParams;
+ * may be NULL).  gsa_ply_write (gsplat_asset.h) then writes the file ExportPlyFile writes
+ * (E/GaussianSplatRendererEditor.cs:394-445).  bake_transform != 0 (rotate SH into world space) is not built:
+ * GS_ERR_UNSUPPORTED_FORMAT.  Blocks. */
+GS_API int gs_export_splats(GsContext *ctx, GsAsset *asset, const GsCutout *cutouts, uint32_t cutout_count,
+                            uint32_t bake_transform, void *dst);
 
 /* ---- test hooks (blocking device->host reads) ----------------------------------- */
 GS_API int gs_readback_order(GsAsset *asset, uint32_t *dst);      /* _SplatSortKeys, N words */

@@ -409,6 +409,28 @@ static void shade_sh(const GsoSplat *s, const float dir_in[3], uint32_t shOrder,
 #undef SH
 }
 
+/* CSExportData, S/SplatUtilities.compute:616-669 with _ExportTransformFlags == 0: LoadSplatData -> ExportSplatData
+ * (= InputSplatData, 62 floats: pos, nor, dc0, sh R/G/B channel-major, opacity, scale, rot wxyz).  log() is libm's here and
+ * the GPU's there: compared with a tolerance, the one place on this path where that is so. */
+void gso_export_data(const GsoAsset *a, const GsoFrame *f, float *out, int threads) {
+  (void)threads;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+  for (int64_t ii = 0; ii < (int64_t)a->splat_count; ++ii) {
+    GsoSplat s;
+    gso_load_splat_data(a, (uint32_t)ii, &s);
+    const int cut = f ? is_splat_cut(f, s.pos) : 0;
+    float *d = out + (size_t)ii * 62;
+    memcpy(d, s.pos, 12);
+    d[3] = d[4] = d[5] = cut ? 1.0f : 0.0f;
+    for (int k = 0; k < 3; ++k) d[6 + k] = (s.col[k] - 0.5f) / 0.2820948f;         /* ColorToSH0 :537-540 */
+    for (int ch = 0; ch < 3; ++ch)
+      for (int j = 0; j < 15; ++j) d[9 + ch * 15 + j] = s.sh[j * 3 + ch];
+    d[54] = logf(s.opacity / fmaxf(1.0f - s.opacity, 1.0e-6f));                  /* InvSigmoid :541-544 */
+    for (int k = 0; k < 3; ++k) d[55 + k] = logf(s.scale[k]);
+    d[58] = s.rot[3]; d[59] = s.rot[0]; d[60] = s.rot[1]; d[61] = s.rot[2];        /* rot.wxyz */
+  }
+}
+
 void gso_calc_view(const GsoAsset *a, const GsoFrame *f, GsoView *view, int threads) {
   /* uniforms, R/GaussianSplatRenderer.cs:586-606 */
   float mv[16], vp[16];

@@ -102,6 +102,9 @@ GSO_API void gso_sort_pairs(uint32_t *keys, uint32_t *payload, uint32_t n, int t
 /* ---- CSCalcViewData (S/SplatUtilities.compute:189-252) ---- */
 GSO_API void gso_calc_view(const GsoAsset *a, const GsoFrame *f, GsoView *view, int threads);
 
+/* ---- CSExportData (S/SplatUtilities.compute:616-669, no baked transform): n x 62 floats, the .ply attribute record; f may be NULL ---- */
+GSO_API void gso_export_data(const GsoAsset *a, const GsoFrame *f, float *out62, int threads);
+
 /* ---- DrawProcedural of RenderGaussianSplats.shader (S/RenderGaussianSplats.shader:35-108,
  *      blend :10-12) into a cleared RT.  rt: W*H*4 floats, premultiplied RGBA; with
  *      blend_mode 0 (fp16 ROP) every value is exactly representable in half. ---- */

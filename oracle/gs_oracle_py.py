@@ -65,6 +65,7 @@ def lib():
         L.gso_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
         L.gso_composite.restype, L.gso_composite.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
         L.gso_max_threads.restype, L.gso_max_threads.argtypes = C.c_int, []
+        L.gso_export_data.restype, L.gso_export_data.argtypes = None, [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_void_p, C.c_int]
         L.gso_bc7_decode_block.restype, L.gso_bc7_decode_block.argtypes = None, [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -134,6 +135,15 @@ def calc_view(asset, fp, threads: int = 1) -> np.ndarray:
     view = np.zeros((asset.splatCount, 10), np.uint32)
     lib().gso_calc_view(C.byref(a), C.byref(f), view.ctypes.data, threads)
     return view
+
+
+def export_data(asset, fp=None, threads: int = 1) -> np.ndarray:
+    """CSExportData: (n, 62) float32 raw .ply attribute records; `fp` only supplies the cutouts."""
+    a = asset_struct(asset)
+    out = np.zeros((asset.splatCount, 62), np.float32)
+    f = frame_struct(fp) if fp is not None else None
+    lib().gso_export_data(C.byref(a), C.byref(f) if f is not None else None, out.ctypes.data, threads)
+    return out
 
 
 def render(view: np.ndarray, order: np.ndarray, width: int, height: int, blend_mode: int = 0, threads: int = 1) -> np.ndarray:

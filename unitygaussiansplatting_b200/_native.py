@@ -100,6 +100,7 @@ NATIVE_SYMBOLS = {
     "gs_readback_keys": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gs_readback_view": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gs_upload_order": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gs_export_splats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "gs_debug_raster_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gs_context_stream": (C.c_void_p, [C.c_void_p]),
     "gs_asset_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
@@ -120,6 +121,7 @@ ASSET_SYMBOLS = {
     "gsa_f32tof16": (C.c_uint32, [C.c_float]),
     "gsa_kmeans": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]),
     "gsa_bc7_encode_block": (None, [C.c_void_p, C.c_void_p]),
+    "gsa_ply_write": (C.c_int64, [C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p]),
 }
 
 

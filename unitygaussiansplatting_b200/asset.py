@@ -114,6 +114,23 @@ def read_ply(path: str) -> np.ndarray:
     return out
 
 
+def write_ply(path: str, records: np.ndarray, deleted_bits=None) -> int:
+    """ExportPlyFile (E/GaussianSplatRendererEditor.cs:394-445): raw attribute records (n x 62, e.g. from
+    GaussianSplatRenderer.EditExportData) -> binary little-endian .ply; deleted / cut-marked records are dropped."""
+    records = np.ascontiguousarray(records, np.float32)
+    if records.ndim != 2 or records.shape[1] != INPUT_SPLAT_FLOATS:
+        raise ValueError("records must be (n, 62) float32")
+    bits = None
+    if deleted_bits is not None:
+        bits = np.ascontiguousarray(deleted_bits, np.uint32)
+        if bits.size < (records.shape[0] + 31) // 32:
+            raise ValueError("deleted_bits is shorter than splat_count / 32 words")
+    n = N.asset_lib().gsa_ply_write(str(path).encode(), records.ctypes.data, records.shape[0], bits.ctypes.data if bits is not None else None)
+    if n < 0:
+        raise OSError("could not write %s" % path)
+    return int(n)
+
+
 def read_spz(path: str) -> np.ndarray:
     """Niantic/Scaniverse .spz -> InputSplatData records, as E/Utils/SPZFileReader.cs unpacks them."""
     lib = N.asset_lib()

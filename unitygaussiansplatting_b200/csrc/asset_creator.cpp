@@ -560,6 +560,31 @@ int64_t gsa_ply_vertex_count(const char *path) {
   return h.count;
 }
 
+// ExportPlyFile, E/GaussianSplatRendererEditor.cs:394-445: header with the 62 float properties in kSplatAttrs order (LF line
+// ends), then every record that is neither deleted (bit set in `deleted_bits`, may be NULL) nor marked cut (nor != 0 --
+// CSExportData's "skipped for export" flag).  `records` are raw .ply attribute values, i.e. gs_export_splats' output.
+int64_t gsa_ply_write(const char *path, const float *records, uint32_t n, const uint32_t *deleted_bits) {
+  if (!path || (!records && n)) return -1;
+  auto alive = [&](uint32_t i) {
+    const bool deleted = deleted_bits && (deleted_bits[i >> 5] & (1u << (i & 31)));
+    const float *r = records + (size_t)i * 62;
+    const bool cut = (r[3] * r[3] + r[4] * r[4] + r[5] * r[5]) > 0.0f;
+    return !deleted && !cut;
+  };
+  int64_t count = 0;
+  for (uint32_t i = 0; i < n; ++i) count += alive(i) ? 1 : 0;
+  FILE *f = fopen(path, "wb");
+  if (!f) return -1;
+  std::string header = "ply\nformat binary_little_endian 1.0\nelement vertex " + std::to_string(count) + "\n";
+  for (const char *name : kSplatAttrs) header += std::string("property float ") + name + "\n";
+  header += "end_header\n";
+  bool ok = fwrite(header.data(), 1, header.size(), f) == header.size();
+  for (uint32_t i = 0; i < n && ok; ++i)
+    if (alive(i)) ok = fwrite(records + (size_t)i * 62, 4, 62, f) == 62;
+  ok = (fclose(f) == 0) && ok;
+  return ok ? count : -1;
+}
+
 int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity) {
   const int64_t n = gsa_ply_vertex_count(path);
   if (n < 0) return (int)n;

@@ -695,6 +695,28 @@ int gs_readback_view(GsAsset *as, void *dst) {
   if (as && !as->view_valid) return fail(as->ctx, GS_ERR_NOT_READY, "_SplatViewData is only materialised by gs_calc_view (gs_frame hands the draw its own records)");
   return readback(as, dst, as ? as->view : nullptr, as ? (size_t)as->av.n * kViewStride : 0);
 }
+int gs_export_splats(GsContext *ctx, GsAsset *as, const GsCutout *cutouts, uint32_t cutout_count, uint32_t bake_transform, void *dst) {
+  if (!ctx || !as || !dst || (cutout_count && !cutouts)) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "null argument");
+  if (as->ctx != ctx) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "asset belongs to another context");
+  if (bake_transform) return fail(ctx, GS_ERR_UNSUPPORTED_FORMAT, "export with a baked transform needs the SH rotation (S/SphericalHarmonics.hlsl), which is not built");
+  GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  GsFrameParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.cutouts = cutouts; fp.cutout_count = cutout_count;
+  int rc = upload_frame_inputs(ctx, as, &fp);
+  if (rc != GS_OK) return rc;
+  float *d_out = nullptr;
+  const size_t bytes = (size_t)as->av.n * 62 * sizeof(float);
+  GS_CUDA_TRY(ctx, cudaMalloc(&d_out, bytes));
+  launch_export_data(as->av, cutout_count, ctx->d_cutouts, d_out, ctx->stream);
+  ctx->launches += 1;
+  cudaError_t e = cudaMemcpyAsync(dst, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "gs_export_splats", __FILE__, __LINE__);
+  return GS_OK;
+}
+
 int gs_upload_order(GsAsset *as, const uint32_t *src) {
   if (!as || !src) return fail(as ? as->ctx : nullptr, GS_ERR_INVALID_ARGUMENT, "null argument");
   GS_CUDA_TRY(as->ctx, cudaMemcpyAsync(as->order, src, (size_t)as->av.n * 4, cudaMemcpyHostToDevice, as->ctx->stream));

@@ -82,6 +82,7 @@ __device__ __forceinline__ uint32_t rect_entries(uint32_t r, const Partition &p)
 
 // ---- launchers (each enqueues on `s`, returns nothing; errors surface via cudaGetLastError) ----
 void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s);
+void launch_export_data(const AssetView &a, uint32_t cutoutCount, const GsCutout *cutouts, float *out, cudaStream_t s);  // gs_export.cu
 void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s);
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
                       uint32_t *rect, float4 *draw, bool cull_undrawable, const Partition &part, cudaStream_t s);

@@ -62,6 +62,11 @@ class GaussianSplatRenderer {
     return ok(gs_frame(m_Ctx, m_Asset, &fp, &options, doSort, rt, cameraTarget));
   }
   bool Sync() { return ok(gs_sync(m_Ctx)); }
+  // EditExportData, R/GaussianSplatRenderer.cs:936-958: n x 62 floats (the .ply attribute record), cut splats marked by nor = 1
+  bool EditExportData(float *dstRecords, bool bakeTransform = false) {
+    return ok(gs_export_splats(m_Ctx, m_Asset, m_Cutouts.empty() ? nullptr : m_Cutouts.data(), (uint32_t)m_Cutouts.size(), bakeTransform ? 1u : 0u,
+                               dstRecords));
+  }
   GsContext *context() const { return m_Ctx; }
   GsAsset *asset() const { return m_Asset; }
 

@@ -248,6 +248,26 @@ class GaussianSplatRenderer:
         N.check(self.context.handle, self._lib.gs_readback_view(self._asset, out.ctypes.data))
         return out
 
+    # ---- export (R/GaussianSplatRenderer.cs:936-958 EditExportData, E/GaussianSplatRendererEditor.cs:394-445 ExportPlyFile) ----
+    def EditExportData(self, bakeTransform: bool = False) -> np.ndarray:
+        """CSExportData on the GPU: (n, 62) float32 raw .ply attribute records; nor = 1 marks splats the cutouts remove."""
+        out = np.empty((self.splatCount, 62), np.float32)
+        arr, count = None, 0
+        if self.m_Cutouts:
+            arr = (N.GsCutout * len(self.m_Cutouts))()
+            for i, (m, tf) in enumerate(self.m_Cutouts):
+                arr[i].mat[:] = colmajor(m).tolist()
+                arr[i].type_and_flags = int(tf)
+            count = len(self.m_Cutouts)
+        N.check(self.context.handle, self._lib.gs_export_splats(self.context.handle, self._asset, arr, count, 1 if bakeTransform else 0,
+                                                                out.ctypes.data))
+        return out
+
+    def ExportPlyFile(self, path: str, bakeTransform: bool = False) -> int:
+        """Writes the .ply the reference's "Export PLY" writes: alive (not deleted, not cut) splats only.  Returns their count."""
+        from .asset import write_ply
+        return write_ply(path, self.EditExportData(bakeTransform), self.m_DeletedBits)
+
     def upload_order(self, order: np.ndarray):
         order = np.ascontiguousarray(order, np.uint32)
         assert order.size == self.splatCount
