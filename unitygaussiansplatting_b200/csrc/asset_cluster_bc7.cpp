@@ -16,12 +16,44 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
+#ifdef __linux__
+#include <sched.h>
+#endif
 #ifdef _OPENMP
 #include <omp.h>
 #endif
 
 namespace {
+
+// Threads worth starting: OpenMP's default, but never more than the CPUs this process may actually use -- its affinity mask
+// and its cgroup CPU quota (a container can show 64 cores and be allowed 8; spinning at barriers then eats the quota).
+int usable_threads() {
+  int t = 1;
+#ifdef _OPENMP
+  t = omp_get_max_threads();
+#endif
+#ifdef __linux__
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) t = std::min(t, std::max(1, CPU_COUNT(&set)));
+  long long quota = -1, period = -1;
+  if (FILE *f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {            // cgroup v2: "<quota|max> <period>"
+    char q[32];
+    if (std::fscanf(f, "%31s %lld", q, &period) == 2 && std::strcmp(q, "max") != 0) quota = std::atoll(q);
+    std::fclose(f);
+  } else {                                                              // cgroup v1
+    if (FILE *g = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (std::fscanf(g, "%lld", &quota) != 1) quota = -1; std::fclose(g); }
+    if (FILE *g = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (std::fscanf(g, "%lld", &period) != 1) period = -1; std::fclose(g); }
+  }
+  if (quota > 0 && period > 0) t = std::min<long long>(t, std::max<long long>(1, (quota + period - 1) / period));
+#endif
+  return std::max(1, t);
+}
+// the k-means++ and mini-batch phases alternate short parallel loops with serial steps thousands of times: a small team
+// keeps the fork/join and barrier cost below the work (each loop is 1-5 ms of arithmetic)
+inline int small_team(int threads) { return std::min(threads, 16); }
 
 inline uint32_t as_u32(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline float as_f32(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
@@ -132,25 +164,33 @@ void make_random_batch(int dim, const float *data, uint32_t data_size, uint32_t 
 }
 
 // KMeansPlusPlus, K:325-411 (+ PickPointIndex K:273-323, CalcDistSqJob K:249-271)
-void kmeans_plus_plus(int dim, int k, const float *data, uint32_t data_size, float *means, float *min_dist_sq, uint32_t &rng) {
+void kmeans_plus_plus(int dim, int k, const float *data, uint32_t data_size, float *means, float *min_dist_sq, uint32_t &rng, int threads) {
+  const int team = small_team(threads);
+  (void)team;
   std::vector<uint8_t> taken(data_size, 0);
   int point = (int)(pcg_random(rng) % data_size);
   taken[point] = 1;
   std::memcpy(means, data + (size_t)point * dim, (size_t)dim * 4);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(team)
   for (int64_t i = 0; i < (int64_t)data_size; ++i)
     if (i != point) min_dist_sq[i] = distance_squared(dim, data + (size_t)i * dim, means);
   constexpr int kSumBatch = 1024;
   const int sum_batches = (int)((data_size + kSumBatch - 1) / kSumBatch);
   std::vector<float> partial(sum_batches);
   int result_count = 1;
+  const float *new_mean = nullptr;   // centre picked in the previous round: its distance update rides in this round's loop
   while (result_count < k) {
-#pragma omp parallel for schedule(static)
+    // ClosestDistanceUpdateJob (K:235-247) for the newest centre, then CalcDistSqJob (K:249-271): one pass per 1024-point
+    // batch, element order inside a batch as in the reference, so sums are the same floats
+#pragma omp parallel for schedule(static) num_threads(team)
     for (int b = 0; b < sum_batches; ++b) {
       const uint32_t i0 = std::min<uint32_t>((uint32_t)b * kSumBatch, data_size), i1 = std::min<uint32_t>((uint32_t)(b + 1) * kSumBatch, data_size);
       float sum = 0;
-      for (uint32_t i = i0; i < i1; ++i)
-        if (!taken[i]) sum += min_dist_sq[i];
+      for (uint32_t i = i0; i < i1; ++i) {
+        if (taken[i]) continue;
+        if (new_mean) min_dist_sq[i] = std::min(min_dist_sq[i], distance_squared(dim, data + (size_t)i * dim, new_mean));
+        sum += min_dist_sq[i];
+      }
       partial[b] = sum;
     }
     float total = 0;
@@ -174,23 +214,16 @@ void kmeans_plus_plus(int dim, int k, const float *data, uint32_t data_size, flo
         if (!taken[i]) { point = (int)i; break; }
     if (point < 0) point = 0;
     taken[point] = 1;
-    float *new_mean = means + (size_t)result_count * dim;
-    std::memcpy(new_mean, data + (size_t)point * dim, (size_t)dim * 4);
+    float *slot = means + (size_t)result_count * dim;
+    std::memcpy(slot, data + (size_t)point * dim, (size_t)dim * 4);
+    new_mean = slot;
     ++result_count;
-    if (result_count < k) {
-#pragma omp parallel for schedule(static)
-      for (int64_t i = 0; i < (int64_t)data_size; ++i) {
-        if (taken[i]) continue;
-        float d = distance_squared(dim, data + (size_t)i * dim, new_mean);
-        min_dist_sq[i] = std::min(min_dist_sq[i], d);
-      }
-    }
   }
 }
 
 // InitializeCentroids, K:507-569
 void initialize_centroids(int dim, const float *data, uint32_t data_size, uint32_t init_batch, uint32_t &rng, int attempts, float *out_means,
-                          int k, std::vector<uint8_t> &picked) {
+                          int k, std::vector<uint8_t> &picked, int threads) {
   init_batch = std::min(init_batch, data_size);
   std::vector<float> centroid_batch((size_t)init_batch * dim), validation_batch((size_t)init_batch * dim);
   make_random_batch(dim, data, data_size, rng, centroid_batch.data(), init_batch, picked);
@@ -199,9 +232,9 @@ void initialize_centroids(int dim, const float *data, uint32_t data_size, uint32
   float min_dist_sum = std::numeric_limits<float>::max();
   MeansT mt;
   for (int ia = 0; ia < attempts; ++ia) {
-    kmeans_plus_plus(dim, k, centroid_batch.data(), init_batch, cur.data(), tmp_dist.data(), rng);
+    kmeans_plus_plus(dim, k, centroid_batch.data(), init_batch, cur.data(), tmp_dist.data(), rng, threads);
     mt.build(dim, k, cur.data());
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
     for (int64_t i = 0; i < (int64_t)init_batch; ++i) nearest_mean(mt, validation_batch.data() + (size_t)i * dim, &tmp_dist[i]);
     float dist_sum = 0;
     for (uint32_t i = 0; i < init_batch; ++i) dist_sum += tmp_dist[i];
@@ -223,7 +256,8 @@ int gsa_kmeans(uint32_t dim, const float *data, uint32_t data_size, uint32_t bat
   batch_size = std::min(data_size, batch_size);
   uint32_t rng = 1;
   std::vector<uint8_t> picked(data_size, 0);
-  initialize_centroids((int)dim, data, data_size, 10u * k, rng, 3, out_means, (int)k, picked);
+  const int threads = usable_threads(), team = small_team(threads);
+  initialize_centroids((int)dim, data, data_size, 10u * k, rng, 3, out_means, (int)k, picked, threads);
 
   std::vector<float> counts(k, 0.0f), batch_points((size_t)batch_size * dim);
   std::vector<int> batch_clusters(batch_size);
@@ -232,7 +266,7 @@ int gsa_kmeans(uint32_t dim, const float *data, uint32_t data_size, uint32_t bat
   const float calc_limit = (float)data_size * passes_over_data;
   for (float calc_done = 0.0f; calc_done < calc_limit; calc_done += (float)batch_size) {
     make_random_batch((int)dim, data, data_size, rng, batch_points.data(), batch_size, picked);
-#pragma omp parallel for schedule(dynamic, 16)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(team)
     for (int64_t i = 0; i < (int64_t)batch_size; ++i) batch_clusters[i] = nearest_mean(mt, batch_points.data() + (size_t)i * dim, nullptr);
     // UpdateCentroidsJob, K:479-505: strictly sequential, per-centre learning rate 1/count
     for (uint32_t i = 0; i < batch_size; ++i) {
@@ -245,7 +279,7 @@ int gsa_kmeans(uint32_t dim, const float *data, uint32_t data_size, uint32_t bat
     }
     for (uint32_t i = 0; i < batch_size; ++i) mt.set(batch_clusters[i], out_means + (size_t)batch_clusters[i] * dim);
   }
-#pragma omp parallel for schedule(dynamic, 256)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
   for (int64_t i = 0; i < (int64_t)data_size; ++i) out_labels[i] = nearest_mean(mt, data + (size_t)i * dim, nullptr);
   return 0;
 }
