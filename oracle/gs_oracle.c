@@ -2,9 +2,12 @@
  * PARITY UNPINNED (no reference golden vectors exist for this path).
  * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared (see oracle/Makefile).
  */
+#define _GNU_SOURCE
 #include "gs_oracle.h"
 
 #include <math.h>
+#include <sched.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -21,12 +24,31 @@ static inline uint32_t rd_u16(const void *base, uint64_t off) { uint16_t v; memc
 static inline float rd_f32(const void *base, uint64_t off) { float v; memcpy(&v, (const uint8_t *)base + off, 4); return v; }
 #define M_(m, r, c) ((m)[(c) * 4 + (r)])
 
+/* Threads worth using: OpenMP's default, capped by the CPUs this process may really use (affinity mask, cgroup CPU quota --
+ * a container can show 128 cores and be allowed 16; oversubscribed OpenMP teams then run several times slower). */
 int gso_max_threads(void) {
+  long long t = 1;
 #ifdef _OPENMP
-  return omp_get_max_threads();
-#else
-  return 1;
+  t = omp_get_max_threads();
 #endif
+#ifdef __linux__
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0 && CPU_COUNT(&set) < t) t = CPU_COUNT(&set);
+  long long quota = -1, period = -1;
+  FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");               /* cgroup v2: "<quota|max> <period>" */
+  if (f) {
+    char q[32];
+    if (fscanf(f, "%31s %lld", q, &period) == 2 && strcmp(q, "max") != 0) quota = atoll(q);
+    fclose(f);
+  } else {                                                      /* cgroup v1 */
+    f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r");
+    if (f) { if (fscanf(f, "%lld", &quota) != 1) quota = -1; fclose(f); }
+    f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+    if (f) { if (fscanf(f, "%lld", &period) != 1) period = -1; fclose(f); }
+  }
+  if (quota > 0 && period > 0 && (quota + period - 1) / period < t) t = (quota + period - 1) / period;
+#endif
+  return t < 1 ? 1 : (int)t;
 }
 
 uint32_t gso_f32tof16(float f) { /* IEEE binary32 -> binary16, round to nearest even */

@@ -30,7 +30,7 @@ namespace {
 
 // Threads worth starting: OpenMP's default, but never more than the CPUs this process may actually use -- its affinity mask
 // and its cgroup CPU quota (a container can show 64 cores and be allowed 8; spinning at barriers then eats the quota).
-int usable_threads() {
+int usable_threads_uncached() {
   int t = 1;
 #ifdef _OPENMP
   t = omp_get_max_threads();
@@ -51,6 +51,7 @@ int usable_threads() {
 #endif
   return std::max(1, t);
 }
+int usable_threads() { static const int t = usable_threads_uncached(); return t; }
 // the k-means++ and mini-batch phases alternate short parallel loops with serial steps thousands of times: a small team
 // keeps the fork/join and barrier cost below the work (each loop is 1-5 ms of arithmetic)
 inline int small_team(int threads) { return std::min(threads, 16); }
@@ -246,6 +247,8 @@ void initialize_centroids(int dim, const float *data, uint32_t data_size, uint32
 }
 
 }  // namespace
+
+int gsa_usable_threads() { return usable_threads(); }
 
 extern "C" {
 

@@ -27,6 +27,8 @@
 #include <parallel/algorithm>
 #endif
 
+int gsa_usable_threads();  // asset_cluster_bc7.cpp: OpenMP default capped by affinity mask and cgroup CPU quota
+
 namespace {
 
 constexpr uint32_t kChunkSize = 256;   // R/GaussianSplatAsset.cs:14
@@ -217,7 +219,7 @@ uint32_t gsa_f32tof16(float v) { return unity_f32tof16(v); }
 
 int gsa_generate(uint32_t kind, uint32_t n, uint32_t seed, GsaInputSplat *out) {
   if (!out || kind > GSA_SCENE_UNIFORM) return -1;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(gsa_usable_threads())
   for (int64_t ii = 0; ii < (int64_t)n; ++ii) {
     uint32_t i = (uint32_t)ii;
     Rng r(seed, i);
@@ -318,7 +320,7 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
     float inv[3];
     for (int k = 0; k < 3; ++k) inv[k] = 1.0f / (bmax[k] - bmin[k]);
     std::vector<std::pair<uint64_t, int32_t>> order(n);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(gsa_usable_threads())
     for (int64_t i = 0; i < (int64_t)n; ++i) {
       uint32_t ip[3];
       for (int k = 0; k < 3; ++k) {
@@ -328,12 +330,12 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
       order[i] = {morton_encode3(ip[0], ip[1], ip[2]), (int32_t)i};
     }
 #ifdef _OPENMP
-    __gnu_parallel::sort(order.begin(), order.end());
+    __gnu_parallel::sort(order.begin(), order.end(), __gnu_parallel::default_parallel_tag(gsa_usable_threads()));
 #else
     std::sort(order.begin(), order.end());
 #endif
     std::vector<GsaInputSplat> copy(splats, splats + n);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(gsa_usable_threads())
     for (int64_t i = 0; i < (int64_t)n; ++i) splats[i] = copy[order[i].second];
   }
 
@@ -343,7 +345,7 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
     const uint32_t k = sh_count(shf, n);
     static const float kPasses[5] = {0.3f, 0.4f, 0.5f, 0.8f, 1.2f};  // Cluster64k..4k, E/...:487-495
     std::vector<float> sh_data((size_t)n * 45), means((size_t)k * 45);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(gsa_usable_threads())
     for (int64_t i = 0; i < (int64_t)n; ++i) std::memcpy(&sh_data[(size_t)i * 45], splats[i].sh, 180);  // GatherSHs :431-440
     sh_labels.resize(n);
     if (gsa_kmeans(45, sh_data.data(), n, 2048, kPasses[shf - 4], means.data(), k, sh_labels.data()) != 0) return -4;
@@ -360,7 +362,7 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
   if (chunked) {
     ChunkInfo *chunks = (ChunkInfo *)chunks_out;
     const int64_t chunk_count = (n + kChunkSize - 1) / kChunkSize;
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel for schedule(dynamic, 64) num_threads(gsa_usable_threads())
     for (int64_t c = 0; c < chunk_count; ++c) {
       float mnp[3], mns[3], mnc[4], mnh[3], mxp[3], mxs[3], mxc[4], mxh[3];
       for (int k = 0; k < 3; ++k) { mnp[k] = mns[k] = mnh[k] = INFINITY; mxp[k] = mxs[k] = mxh[k] = -INFINITY; }
@@ -426,7 +428,7 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
   // BC7 is encoded from the float image, 4x4 texels at a time (E/...:887-912)
   std::vector<float> image;
   if (cf == 3) image.assign((size_t)sz.tex_width * sz.tex_height * 4, 0.0f);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(gsa_usable_threads())
   for (int64_t i = 0; i < (int64_t)n; ++i) {
     const GsaInputSplat &s = splats[i];
     emit_vector(s.pos, (uint8_t *)pos_out + (uint64_t)i * pstride, pf);
@@ -476,7 +478,7 @@ int gsa_create_asset(GsaInputSplat *splats, uint32_t n, uint32_t pf, uint32_t sf
   }
   if (cf == 3) {
     const uint32_t bw = sz.tex_width / 4, bh = sz.tex_height / 4;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(gsa_usable_threads())
     for (int64_t b = 0; b < (int64_t)bw * bh; ++b) {
       const uint32_t bx = (uint32_t)(b % bw), by = (uint32_t)(b / bw);
       float blk[64];
@@ -608,7 +610,7 @@ int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity) {
   const size_t got = fread(raw.data(), 1, raw.size(), f);
   fclose(f);
   if (got != raw.size()) return -4;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(gsa_usable_threads())
   for (int64_t i = 0; i < n; ++i) {
     float d[62];
     const uint8_t *src = raw.data() + (size_t)i * h.stride;
@@ -684,7 +686,7 @@ int gsa_spz_read(const char *path, GsaInputSplat *out, uint32_t capacity) {
   gzclose(gz);
   if (!ok) return -4;
   const float fractScale = 1.0f / (float)(1 << fractBits);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(gsa_usable_threads())
   for (int64_t i = 0; i < n; ++i) {  // UnpackDataJob, :125-195
     GsaInputSplat s;
     std::memset(&s, 0, sizeof(s));

@@ -300,11 +300,12 @@ static int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const G
       ctx->raster_tiles_cur = rtiles;
     }
   }
-  launch_binning(fc, opt, as->av.n, as->order, as->rect, ctx->bin, ctx->sort, ctx->stream);
+  int bin_passes = 0;
+  const BinScratch lists = launch_binning(fc, opt, as->av.n, as->order, as->rect, ctx->bin, ctx->sort, ctx->stream, &bin_passes);
   rec(ctx, EV_BIN1);
-  launch_raster(fc, opt, as->draw, ctx->bin, d_rt, pitch, fmt, ctx->stream);
+  launch_raster(fc, opt, as->draw, lists, d_rt, pitch, fmt, ctx->stream);
   rec(ctx, EV_RASTER1);
-  ctx->launches += 1 + 2 + 3;  // bin_emit, 2 sort passes, bin_ranges, tile_order, raster
+  ctx->launches += 1 + bin_passes + 3;  // bin_emit, 1-2 sort passes, bin_ranges, tile_order, raster
   GS_CUDA_TRY(ctx, cudaGetLastError());
   return GS_OK;
 }

@@ -115,8 +115,9 @@ struct BinScratch {
   uint32_t *tile_cost, *tile_order;   // per raster tile: last frame's cost, this frame's launch order
   uint32_t capacity;
 };
-void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
-                    const BinScratch &bs, const SortScratch &sc, cudaStream_t s);
+// returns the scratch view whose tile_keys / tile_vals hold the bin-sorted lists (launch_raster's input)
+BinScratch launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
+                          const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *sort_passes);
 void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
                    uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s);
 extern unsigned long long *g_raster_stats;   // diagnostics, see GS_RASTER_STATS

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
                                                   Partition part, uint32_t tilesX, volatile uint32_t *status, uint32_t *ticket,
                                                   uint32_t nblocks, uint32_t capacity, uint32_t *__restrict__ keys,
                                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ entry_count,
-                                                  uint32_t *__restrict__ ghist, uint32_t digit_bits) {
+                                                  uint32_t *__restrict__ ghist, uint32_t digit_bits, bool two_pass) {
   __shared__ uint32_t s_w[8];
   __shared__ uint32_t s_block, s_excl;
   __shared__ uint32_t s_dh[512];   // digit histograms of the two sort passes over the tile ids we emit
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
         keys[o] = tile;
         vals[o] = oid;
         atomicAdd(&s_dh[tile & dmask], 1u);
-        atomicAdd(&s_dh[256 + ((tile >> digit_bits) & dmask)], 1u);
+        if (two_pass) atomicAdd(&s_dh[256 + ((tile >> digit_bits) & dmask)], 1u);
       }
     }
     off += T;
@@ -162,20 +162,32 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
   }
 }
 
-int bin_sort_bits(uint32_t bins) { return bins <= 1024u ? 5 : bins <= 4096u ? 6 : bins <= 16384u ? 7 : 8; }
+// digit width and pass count of the stable sort by bin id: one pass while the bin count fits a digit (<= 256 bins, e.g.
+// 1200x797 = 19x13), else two passes of the narrowest digit that covers it
+static void bin_sort_plan(uint32_t bins, int *bits, int *passes) {
+  if (bins <= 256u) { *passes = 1; *bits = bins <= 32u ? 5 : bins <= 64u ? 6 : bins <= 128u ? 7 : 8; return; }
+  *passes = 2;
+  *bits = bins <= 1024u ? 5 : bins <= 4096u ? 6 : bins <= 16384u ? 7 : 8;
+}
 
-void launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
-                    const BinScratch &bs, const SortScratch &sc, cudaStream_t s) {
+BinScratch launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
+                          const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *sort_passes) {
   const Partition part = make_partition(opt);
   const uint32_t tiles = fc.binsX * fc.binsY;
-  if (!n) { cudaMemsetAsync(bs.entry_count, 0, 16, s); return; }
+  if (sort_passes) *sort_passes = 0;
+  if (!n) { cudaMemsetAsync(bs.entry_count, 0, 16, s); return bs; }
   const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
   cudaMemsetAsync(bs.block_sums, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
-  const int bits = bin_sort_bits(tiles);
+  int bits, passes;
+  bin_sort_plan(tiles, &bits, &passes);
+  if (sort_passes) *sort_passes = passes;
   cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
   k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, n, part, fc.binsX, bs.block_sums + 1, bs.block_sums, nblocks, bs.capacity,
-                                     bs.tile_keys, bs.tile_vals, bs.entry_count, sc.ghist, (uint32_t)bits);
-  launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, 2, bits, true, sc, s);
+                                     bs.tile_keys, bs.tile_vals, bs.entry_count, sc.ghist, (uint32_t)bits, passes == 2);
+  launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, passes, bits, true, sc, s);
+  BinScratch sorted = bs;   // an odd number of passes leaves the sorted lists in the sorter's ping-pong buffers
+  if (passes & 1) { sorted.tile_keys = sc.alt_keys; sorted.tile_vals = sc.alt_vals; }
+  return sorted;
 }
 
 // ---- 2. raster ---------------------------------------------------------------------------------
