@@ -118,13 +118,15 @@ typedef struct GsImage {
  * half after EVERY splat.  GS_BLEND_FP32 keeps dst in float32 registers and rounds once. */
 typedef enum GsBlendMode { GS_BLEND_FP16_ROP = 0, GS_BLEND_FP32 = 1 } GsBlendMode;
 
+#define GS_BAND_PIXELS 64u /* height of one partition row = edge of a binning cell (csrc/gs_common.cuh kBin) */
+
 typedef struct GsRenderOptions {
   uint32_t blend_mode;        /* GsBlendMode */
-  uint32_t band_packed;       /* 1: rt holds only this partition's rows, packed: own 32-pixel row k -> pixel rows
-                                 [32k, 32k+32); rt->height must be 32 * (number of own rows).  This is the
+  uint32_t band_packed;       /* 1: rt holds only this partition's rows, packed: own 64-pixel row k -> pixel rows
+                                 [64k, 64k+64); rt->height must be 64 * (number of own rows).  This is the
                                  send buffer of the all-gather. */
   /* Screen-tile partition for multi-GPU: this context composites only
-   * 32-pixel rows r with (r / band_rows) % partition_count == partition_index.
+   * 64-pixel rows (GS_BAND_PIXELS, the binning cell) r with (r / band_rows) % partition_count == partition_index.
    * partition_count 0 or 1 = whole image. */
   uint32_t partition_index, partition_count, band_rows, reserved1;
 } GsRenderOptions;
@@ -192,7 +194,7 @@ GS_API int gs_frame(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp,
 
 /* Multi-GPU epilogue: `gathered` is the all-gather of every partition's band-packed
  * render target, [partition_count][rows_per_partition][width] pixels in DEVICE memory, where
- * rows_per_partition = 32 * max over partitions of own 32-pixel rows.  Writes the assembled width x height
+ * rows_per_partition = 64 * max over partitions of own 64-pixel rows.  Writes the assembled width x height
  * image (device or host) in normal row order. */
 GS_API int gs_unshuffle_bands(GsContext *ctx, const void *gathered, uint32_t partition_count, uint32_t band_rows,
                               uint32_t rows_per_partition, uint32_t pixel_format, GsImage *out);

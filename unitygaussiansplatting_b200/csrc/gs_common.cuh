@@ -17,7 +17,7 @@ namespace gs {
 constexpr int kChunkSize = 256;     // R/GaussianSplatAsset.cs:14, S/GaussianSplatting.hlsl:207
 constexpr int kTexWidth = 2048;     // R/GaussianSplatAsset.cs:15, S/GaussianSplatting.hlsl:181
 constexpr int kTile = 16;           // raster CTA tile edge in pixels
-constexpr int kBin = 64;            // binning cell edge in pixels: one list per 32x32 cell, shared by its four 16x16 raster tiles
+constexpr int kBin = 64;            // binning cell edge in pixels: one list per 64x64 cell, shared by its sixteen 16x16 raster tiles
 constexpr int kViewStride = 40;     // sizeof(SplatViewData), S/GaussianSplatting.hlsl:610-615
 
 // SplatChunkInfo, S/GaussianSplatting.hlsl:196-202 (64 bytes)
@@ -28,6 +28,7 @@ struct __align__(16) Chunk {
   uint32_t shR, shG, shB;
 };
 static_assert(sizeof(Chunk) == 64, "chunk layout");
+static_assert(kBin == (int)GS_BAND_PIXELS, "the public header documents the partition row height");
 
 // SplatViewData as two 16-byte vectors + one 8-byte vector
 struct ViewRec {
@@ -49,7 +50,7 @@ struct FrameConsts {
   float screenW, screenH;
   uint32_t shOrder, shOnly;
   uint32_t cutoutCount, bitsValid;
-  uint32_t binsX, binsY;   // 32-pixel binning cells
+  uint32_t binsX, binsY;   // kBin-pixel binning cells
 };
 
 struct AssetView {     // device pointers + formats of one uploaded asset

@@ -39,7 +39,7 @@ __device__ __forceinline__ bool splat_footprint(float4 clip, float a1x, float a1
   return true;
 }
 
-// Pixel rows/cols whose centres can be touched -> inclusive rectangle of 32-pixel bins packed x0|y0<<8|x1<<16|y1<<24.
+// Pixel rows/cols whose centres can be touched -> inclusive rectangle of kBin-pixel bins packed x0|y0<<8|x1<<16|y1<<24.
 __device__ __forceinline__ uint32_t footprint_tile_rect(const SplatFootprint &fp, const FrameConsts &fc) {
   float x0 = fmaxf(ceilf(fp.cx - fp.hx - 0.5f), 0.0f), x1 = fminf(floorf(fp.cx + fp.hx - 0.5f), fc.screenW - 1.0f);
   float y0 = fmaxf(ceilf(fp.cy - fp.hy - 0.5f), 0.0f), y1 = fminf(floorf(fp.cy + fp.hy - 0.5f), fc.screenH - 1.0f);

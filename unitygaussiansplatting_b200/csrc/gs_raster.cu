@@ -5,7 +5,7 @@
 // (S/RenderGaussianSplats.shader:10-12,35-108; draw call R/GaussianSplatRenderer.cs:156-165).
 // A CUDA device has neither rasteriser nor ROP, so the same pixels are produced by:
 //   1. bin   -- walk the splats in sorted order; each emits one (bin id, splat id) entry per
-//               32x32-pixel bin its visible footprint can touch (rect written by k_calc_view).
+//               64x64-pixel bin its visible footprint can touch (rect written by k_calc_view).
 //               Bins are coarser than the 16x16 raster tiles on purpose: 2.5x fewer entries to
 //               emit and sort, and the per-warp ballot cull below makes a foreign entry cost 1/32
 //               of an evaluation.  Emission order == depth order, so one STABLE 16-bit radix sort
@@ -309,7 +309,7 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   }
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // grid: x = 16-pixel tile column, y = 2 * (own 32-pixel bin row) + (upper | lower tile row of that bin row)
+  // 1-D grid over raster tiles: tile = (16-pixel column, R * own 64-pixel bin row + tile row inside that bin row)
   constexpr uint32_t R = kBin / kTile;   // raster tiles per bin edge
   // launch order != raster order: CTA i takes tile order[i] (k_tile_order: most expensive first, by last frame's cost),
   // so the expensive tiles start early instead of forming the tail

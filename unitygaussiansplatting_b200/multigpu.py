@@ -1,7 +1,7 @@
 """Screen-tile partition across the GPUs of one box (the reference is single-GPU).
 
 Every rank holds the whole asset, sorts and view-calcs it redundantly, and composites only its own
-bands of 32-pixel bin rows (interleaved round-robin for load balance).  Each rank renders straight
+bands of 64-pixel bin rows (interleaved round-robin for load balance).  Each rank renders straight
 into its slice of the all-gather buffer ("band-packed": own bin row k -> pixel rows [32k,32k+32)),
 ONE all-gather moves the bands, and gs_unshuffle_bands assembles the image.  torch.distributed is
 plumbing only (process group + the collective); the partition arithmetic below is mirrored by the
@@ -14,7 +14,7 @@ from dataclasses import dataclass
 
 from . import _native as N
 
-TILE = 64   # band granularity in pixels: the library bins (and partitions) in 32-pixel rows (csrc/gs_common.cuh kBin)
+TILE = 64   # band granularity in pixels: the library bins (and partitions) in 64-pixel rows (csrc/gs_common.cuh kBin)
 
 
 @dataclass
