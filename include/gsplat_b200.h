@@ -226,6 +226,32 @@ GS_API int gs_upload_order(GsAsset *asset, const uint32_t *src);  /* seed a prev
  * [1] warp cull ballots, [2] warp candidates, [3] warp evaluations, [4] pixel blends, [5] list entries x warps. */
 GS_API int gs_debug_raster_stats(GsContext *ctx, uint64_t out[8]);
 
+/* ---- Unity render-thread entry -------------------------------------- */
+/* Unity executes native GPU work on its render thread through CommandBuffer.IssuePluginEventAndData(func, eventId, data)
+ * (the reference records everything into CommandBuffers, R/GaussianSplatRenderer.cs:108-211).  `func` is what
+ * gs_unity_get_render_event_func returns (signature of Unity's UnityRenderingEventAndData); `data` points to a
+ * GsUnityFrameEvent the managed side keeps alive (pinned) until the command buffer has executed.  The callback runs
+ * the requested entry point and stores its GsStatus in `status` -- "log and skip", never a throw across the boundary. */
+typedef enum GsUnityEvent {
+  GS_UNITY_EVENT_FRAME = 1,   /* gs_frame(ctx, asset, &params, &options, do_sort, has_rt ? &rt : NULL, has_camera_target ? &camera_target : NULL) */
+  GS_UNITY_EVENT_SYNC = 2     /* gs_sync(ctx) */
+} GsUnityEvent;
+
+typedef struct GsUnityFrameEvent {
+  GsContext *ctx;
+  GsAsset *asset;
+  GsFrameParams params;
+  GsRenderOptions options;
+  int32_t do_sort;            /* m_FrameCounter % m_SortNthFrame == 0 */
+  int32_t status;             /* out: GsStatus of the call (GS_ERR_NOT_READY until the event has run) */
+  uint32_t has_rt, has_camera_target;
+  GsImage rt, camera_target;
+} GsUnityFrameEvent;
+
+typedef void (*GsUnityRenderEventAndDataFunc)(int event_id, void *data);
+GS_API GsUnityRenderEventAndDataFunc gs_unity_get_render_event_func(void);
+GS_API uint32_t gs_unity_frame_event_size(void);   /* sizeof(GsUnityFrameEvent), for the managed side's layout check */
+
 /* ---- device-pointer access for zero-copy hosts (torch / CUDA-Vulkan interop) ----- */
 GS_API void *gs_context_stream(GsContext *ctx);
 GS_API void *gs_asset_device_ptr(GsAsset *asset, int which); /* 0 order, 1 keys, 2 view */

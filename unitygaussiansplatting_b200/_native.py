@@ -62,6 +62,16 @@ class GsRenderOptions(C.Structure):
                 ("partition_count", C.c_uint32), ("band_rows", C.c_uint32), ("reserved1", C.c_uint32)]
 
 
+class GsUnityFrameEvent(C.Structure):   # include/gsplat_b200.h: the payload of CommandBuffer.IssuePluginEventAndData
+    _fields_ = [("ctx", C.c_void_p), ("asset", C.c_void_p), ("params", GsFrameParams), ("options", GsRenderOptions),
+                ("do_sort", C.c_int32), ("status", C.c_int32), ("has_rt", C.c_uint32), ("has_camera_target", C.c_uint32),
+                ("rt", GsImage), ("camera_target", GsImage)]
+
+
+GS_UNITY_EVENT_FRAME, GS_UNITY_EVENT_SYNC = 1, 2
+GsUnityRenderEventAndDataFunc = C.CFUNCTYPE(None, C.c_int, C.c_void_p)
+
+
 class GsStageTimes(C.Structure):
     _fields_ = [("distances_ms", C.c_float), ("sort_ms", C.c_float), ("view_ms", C.c_float), ("bin_ms", C.c_float),
                 ("raster_ms", C.c_float), ("composite_ms", C.c_float), ("total_ms", C.c_float),
@@ -100,6 +110,8 @@ NATIVE_SYMBOLS = {
     "gs_readback_keys": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gs_readback_view": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gs_upload_order": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gs_unity_get_render_event_func": (GsUnityRenderEventAndDataFunc, []),
+    "gs_unity_frame_event_size": (C.c_uint32, []),
     "gs_export_splats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "gs_debug_raster_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gs_context_stream": (C.c_void_p, [C.c_void_p]),

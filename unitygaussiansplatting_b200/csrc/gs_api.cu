@@ -725,6 +725,25 @@ int gs_upload_order(GsAsset *as, const uint32_t *src) {
   return GS_OK;
 }
 
+// ---- Unity render-thread entry: IssuePluginEventAndData -> gs_frame / gs_sync ----
+static void gs_unity_on_render_event(int event_id, void *data) {
+  GsUnityFrameEvent *ev = static_cast<GsUnityFrameEvent *>(data);
+  if (!ev) return;
+  switch (event_id) {
+    case GS_UNITY_EVENT_FRAME:
+      ev->status = gs_frame(ev->ctx, ev->asset, &ev->params, &ev->options, ev->do_sort, ev->has_rt ? &ev->rt : nullptr,
+                            ev->has_camera_target ? &ev->camera_target : nullptr);
+      break;
+    case GS_UNITY_EVENT_SYNC:
+      ev->status = gs_sync(ev->ctx);
+      break;
+    default:
+      ev->status = fail(ev->ctx, GS_ERR_INVALID_ARGUMENT, "unknown render event id");
+  }
+}
+GsUnityRenderEventAndDataFunc gs_unity_get_render_event_func(void) { return gs_unity_on_render_event; }
+uint32_t gs_unity_frame_event_size(void) { return (uint32_t)sizeof(GsUnityFrameEvent); }
+
 int gs_debug_raster_stats(GsContext *ctx, uint64_t out[8]) {
   if (!ctx || !out) return GS_ERR_INVALID_ARGUMENT;
   memset(out, 0, 64);
