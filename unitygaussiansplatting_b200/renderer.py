@@ -114,6 +114,15 @@ def _inverse_cached(m: np.ndarray) -> np.ndarray:
     return hit
 
 
+def cutout_array(cutouts):
+    """[(4x4 matrix = cutout worldToLocal * renderer localToWorld, type_and_flags)] -> GsCutout[] (R/GaussianCutout.cs:26-40)."""
+    arr = (N.GsCutout * len(cutouts))()
+    for i, (m, tf) in enumerate(cutouts):
+        arr[i].mat[:] = colmajor(m).tolist()
+        arr[i].type_and_flags = int(tf)
+    return arr
+
+
 def make_frame_params(cam: Camera, localToWorld=None, splat_scale=1.0, opacity_scale=1.0, sh_order=3, sh_only=False, cutouts=None,
                       deleted_bits=None, splat_count=0):
     """The uniforms C# binds in CalcViewData / SortPoints (R/GaussianSplatRenderer.cs:586-606,617-631).
@@ -132,10 +141,7 @@ def make_frame_params(cam: Camera, localToWorld=None, splat_scale=1.0, opacity_s
     fp.sh_order, fp.sh_only = int(sh_order), 1 if sh_only else 0
     keep = []
     if cutouts:
-        arr = (N.GsCutout * len(cutouts))()
-        for i, (m, tf) in enumerate(cutouts):
-            arr[i].mat[:] = colmajor(m).tolist()
-            arr[i].type_and_flags = int(tf)
+        arr = cutout_array(cutouts)
         fp.cutouts, fp.cutout_count = C.cast(arr, C.c_void_p), len(cutouts)
         keep.append(arr)
     if deleted_bits is not None:
@@ -252,13 +258,8 @@ class GaussianSplatRenderer:
     def EditExportData(self, bakeTransform: bool = False) -> np.ndarray:
         """CSExportData on the GPU: (n, 62) float32 raw .ply attribute records; nor = 1 marks splats the cutouts remove."""
         out = np.empty((self.splatCount, 62), np.float32)
-        arr, count = None, 0
-        if self.m_Cutouts:
-            arr = (N.GsCutout * len(self.m_Cutouts))()
-            for i, (m, tf) in enumerate(self.m_Cutouts):
-                arr[i].mat[:] = colmajor(m).tolist()
-                arr[i].type_and_flags = int(tf)
-            count = len(self.m_Cutouts)
+        arr = cutout_array(self.m_Cutouts) if self.m_Cutouts else None
+        count = len(self.m_Cutouts) if self.m_Cutouts else 0
         N.check(self.context.handle, self._lib.gs_export_splats(self.context.handle, self._asset, arr, count, 1 if bakeTransform else 0,
                                                                 out.ctypes.data))
         return out
