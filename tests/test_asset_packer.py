@@ -228,3 +228,31 @@ def test_spz_reader_follows_the_importer(g, tmp_path):
         f.write(struct.pack("<IIII", 0x5053474E, 3, n, 0))        # unsupported version
     with pytest.raises(ValueError):
         g.read_spz(tmp_path / "b.spz")
+
+
+@pytest.mark.parametrize("quality", ["VeryLow", "Medium", "VeryHigh"])
+def test_asset_files_round_trip(g, tmp_path, quality):
+    """save_asset writes the importer's file set (E/GaussianSplatAssetCreator.cs:300-305 + the serialized fields of
+    R/GaussianSplatAsset.cs:18-22,205-216); load_asset reads it back identically and rejects damaged sets."""
+    n = 9000
+    a = g.synthetic_asset(g.SCENE_CLUSTERED, n, 0x5EED0061, quality)
+    g.save_asset(a, tmp_path, "scene")
+    names = sorted(p.name for p in tmp_path.iterdir())
+    expect = ["scene.asset", "scene_col.bytes", "scene_oth.bytes", "scene_pos.bytes", "scene_shs.bytes"] + (["scene_chk.bytes"] if quality != "VeryHigh" else [])
+    assert names == sorted(expect)
+    b = g.load_asset(tmp_path, "scene")
+    assert (b.splatCount, b.posFormat, b.scaleFormat, b.colorFormat, b.shFormat) == (a.splatCount, a.posFormat, a.scaleFormat, a.colorFormat, a.shFormat)
+    for attr in ("posData", "otherData", "colorData", "shData"):
+        assert np.array_equal(getattr(a, attr), getattr(b, attr))
+    assert (a.chunkData is None) == (b.chunkData is None) and (a.chunkData is None or np.array_equal(a.chunkData, b.chunkData))
+    assert np.allclose(a.boundsMin, b.boundsMin) and np.allclose(a.boundsMax, b.boundsMax)
+    # a Unity-written .asset has many more lines (script reference, GUID'd TextAsset references, cameras): only the scalars matter
+    text = (tmp_path / "scene.asset").read_text()
+    (tmp_path / "scene.asset").write_text(text + "  m_PosData: {fileID: 4900000, guid: 0123456789abcdef0123456789abcdef, type: 3}\n  m_Cameras: []\n")
+    assert g.load_asset(tmp_path, "scene").splatCount == n
+    (tmp_path / "scene_pos.bytes").write_bytes(b"\0" * 16)
+    with pytest.raises(ValueError):
+        g.load_asset(tmp_path, "scene")
+    (tmp_path / "scene.asset").write_text(text.replace("m_FormatVersion: 20231020", "m_FormatVersion: 20230101"))
+    with pytest.raises(ValueError):
+        g.load_asset(tmp_path, "scene")

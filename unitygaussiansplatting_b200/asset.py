@@ -169,5 +169,76 @@ def create_asset(splats: np.ndarray, quality: str = "Medium", formats=None) -> G
                               bounds[:3].copy(), bounds[3:].copy())
 
 
+# ---- on-disk form: the five .bytes blobs + the serialized ScriptableObject (E/GaussianSplatAssetCreator.cs:296-330) ----
+FORMAT_VERSION = 20231020  # GaussianSplatAsset.kCurrentVersion, R/GaussianSplatAsset.cs:13
+_BLOBS = (("chunkData", "chk"), ("posData", "pos"), ("otherData", "oth"), ("colorData", "col"), ("shData", "shs"))
+
+
+def save_asset(asset: GaussianSplatAsset, folder, name: str) -> None:
+    """Writes `<name>_chk|pos|oth|col|shs.bytes` (the importer's file names, E/...:300-305) and `<name>.asset`: the fields
+    Unity serializes for a GaussianSplatAsset (R/GaussianSplatAsset.cs:18-22,205-216) in its text-YAML form.  The object
+    references to the TextAssets are by GUID in a Unity project; here they are by file name, which load_asset resolves."""
+    from pathlib import Path
+    folder = Path(folder)
+    folder.mkdir(parents=True, exist_ok=True)
+    for attr, tag in _BLOBS:
+        blob = getattr(asset, attr)
+        if blob is not None and blob.nbytes:
+            (folder / ("%s_%s.bytes" % (name, tag))).write_bytes(np.ascontiguousarray(blob).tobytes())
+    v = lambda a: "{x: %r, y: %r, z: %r}" % tuple(float(t) for t in a)
+    lines = ["%YAML 1.1", "%TAG !u! tag:unity3d.com,2011:", "--- !u!114 &11400000", "MonoBehaviour:", "  m_Name: %s" % name,
+             "  m_FormatVersion: %d" % FORMAT_VERSION, "  m_SplatCount: %d" % asset.splatCount,
+             "  m_BoundsMin: %s" % v(asset.boundsMin), "  m_BoundsMax: %s" % v(asset.boundsMax),
+             "  m_PosFormat: %d" % int(asset.posFormat), "  m_ScaleFormat: %d" % int(asset.scaleFormat),
+             "  m_SHFormat: %d" % int(asset.shFormat), "  m_ColorFormat: %d" % int(asset.colorFormat)]
+    (folder / (name + ".asset")).write_text("\n".join(lines) + "\n")
+
+
+def load_asset(folder, name: str) -> GaussianSplatAsset:
+    """Reads what save_asset -- or the Unity importer -- wrote: `<name>.asset` (YAML; only the m_* scalars are needed) and the
+    `.bytes` blobs next to it.  Sizes are checked against the formats (R/GaussianSplatAsset.cs:174-203)."""
+    import re
+    from pathlib import Path
+    folder = Path(folder)
+    text = (folder / (name + ".asset")).read_text()
+
+    def field(key, cast=int):
+        m = re.search(r"^\s*%s:\s*(\S+)\s*$" % re.escape(key), text, re.M)
+        if not m:
+            raise ValueError("%s.asset has no %s" % (name, key))
+        return cast(m.group(1))
+
+    def vec(key):
+        m = re.search(r"^\s*%s:\s*\{x:\s*([^,]+),\s*y:\s*([^,]+),\s*z:\s*([^}]+)\}" % re.escape(key), text, re.M)
+        return np.array([float(t) for t in m.groups()], np.float32) if m else np.zeros(3, np.float32)
+
+    version = field("m_FormatVersion")
+    if version != FORMAT_VERSION:
+        raise ValueError("asset format version %d, expected %d (HasValidAsset rejects it too, R/GaussianSplatRenderer.cs:361-368)" % (version, FORMAT_VERSION))
+    n = field("m_SplatCount")
+    pf, sf = VectorFormat(field("m_PosFormat")), VectorFormat(field("m_ScaleFormat"))
+    shf, cf = SHFormat(field("m_SHFormat")), ColorFormat(field("m_ColorFormat"))
+    blobs = {}
+    for attr, tag in _BLOBS:
+        path = folder / ("%s_%s.bytes" % (name, tag))
+        blobs[attr] = np.fromfile(path, np.uint8) if path.exists() else None
+    for attr in ("posData", "otherData", "colorData", "shData"):
+        if blobs[attr] is None:
+            raise ValueError("missing %s blob of %s" % (attr, name))
+    sz = N.GsaSizes()
+    if N.asset_lib().gsa_calc_sizes(n, int(pf), int(sf), int(cf), int(shf), C.byref(sz)) != 0:
+        raise ValueError("unsupported format combination in %s.asset" % name)
+    # pos / other are padded to 8 bytes by the importer; a clustered-SH file may also carry CalcSHDataSize's n*2 slack
+    need = {"posData": n * (12, 6, 4, 2)[int(pf)], "otherData": sz.other_bytes - 7, "colorData": sz.color_bytes, "shData": sz.sh_bytes}
+    for attr, least in need.items():
+        if blobs[attr].nbytes < least:
+            raise ValueError("%s of %s is %d bytes, its format needs %d" % (attr, name, blobs[attr].nbytes, least))
+    uses_chunks = sz.chunk_bytes != 0
+    if uses_chunks and (blobs["chunkData"] is None or blobs["chunkData"].nbytes < sz.chunk_bytes):
+        raise ValueError("%s needs chunk data (lossy formats) but has none / too little" % name)
+    return GaussianSplatAsset(n, pf, sf, cf, shf, blobs["posData"], blobs["otherData"], blobs["colorData"], blobs["shData"],
+                              blobs["chunkData"] if uses_chunks else None, vec("m_BoundsMin"), vec("m_BoundsMax"))
+
+
 def synthetic_asset(kind: int, n: int, seed: int, quality: str = "Medium") -> GaussianSplatAsset:
     return create_asset(generate_input_splats(kind, n, seed), quality)
