@@ -2,7 +2,7 @@
 
 Every rank holds the whole asset, sorts and view-calcs it redundantly, and composites only its own
 bands of 64-pixel bin rows (interleaved round-robin for load balance).  Each rank renders straight
-into its slice of the all-gather buffer ("band-packed": own bin row k -> pixel rows [32k,32k+32)),
+into its slice of the all-gather buffer ("band-packed": own bin row k -> pixel rows [64k,64k+64)),
 ONE all-gather moves the bands, and gs_unshuffle_bands assembles the image.  torch.distributed is
 plumbing only (process group + the collective); the partition arithmetic below is mirrored by the
 device code in csrc/gs_raster.cu (struct Partition) and tested against it.
