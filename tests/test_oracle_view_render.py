@@ -209,3 +209,51 @@ def test_composite_formula(O):
     assert np.abs(out[..., :3] - want)[m].max() < 2e-6
     assert np.abs(out[..., 3] - (a * a + bg[..., 3] * (1 - a)))[m].max() < 2e-6
     assert np.array_equal(out[0, 0], bg[0, 0])
+
+
+def test_anisotropic_splats_match_the_textbook_conic_form(g, O):
+    """Independent restatement, float64: the 3DGS paper's EWA projection (cov2d = J W Sigma W^T J^T + 0.3 I) and its pixel
+    weight alpha = o * exp(-1/2 d^T cov2d^-1 d).  The reference draws the same Gaussian as an oriented quad with
+    exp(-|q|^2) in eigen-coordinates (S/SplatUtilities.compute:107-162, S/RenderGaussianSplats.shader:54-86); for rotated,
+    anisotropic splats well inside the screen (no clamp, no lambda2 floor, inside the +-2 quad) the two must agree."""
+    rng = np.random.default_rng(5)
+    W, H = 320, 240
+    cam = camera(g, W, H, fov=50.0, pos=(0.2, -0.1, -3.0))
+    for _ in range(6):
+        q = rng.standard_normal(4)
+        q /= np.linalg.norm(q)
+        scale = np.exp(rng.uniform(np.log(0.03), np.log(0.25), 3))
+        asset = one_splat(g, pos=tuple(rng.uniform(-0.3, 0.3, 3)), scale=tuple(scale), quat=tuple(q), opacity=0.7, dc0=(0.5, 0.6, 0.7))
+        s = O.load_splat(asset, 0)                               # rotation as stored (10.10.10.2), not as requested
+        fp, _ = g.make_frame_params(cam, sh_order=0)
+        view = O.calc_view(asset, fp)
+        v = view_fields(view)
+        rt = O.render(view, np.arange(1, dtype=np.uint32), W, H, blend_mode=1)
+        x, y, z, w = (float(t) for t in s["rot"])
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        S2 = np.diag(np.asarray(s["scale"], np.float64) ** 2)
+        V = np.array(fp.mat_view[:], np.float64).reshape(4, 4).T
+        P = np.array(fp.mat_proj_gpu[:], np.float64).reshape(4, 4).T
+        t = V @ np.array(list(s["pos"]) + [1.0], np.float64)
+        f = W * P[0, 0] / 2
+        J = np.array([[f / t[2], 0, -f * t[0] / t[2] ** 2], [0, f / t[2], -f * t[1] / t[2] ** 2]])
+        cov = J @ V[:3, :3] @ R @ S2 @ R.T @ V[:3, :3].T @ J.T + 0.3 * np.eye(2)
+        assert np.linalg.eigvalsh(cov)[0] > 0.2                  # the lambda2 >= 0.1 floor is not in play
+        clip = P @ t
+        cx, cy = (clip[0] / clip[3] * 0.5 + 0.5) * W, (0.5 - 0.5 * clip[1] / clip[3]) * H
+        ys, xs = np.mgrid[0:H, 0:W]
+        # cov2d lives in view space (y up); the render-into-texture projection flips y, hence +(py - cy) here
+        d = np.stack([xs + 0.5 - cx, (ys + 0.5) - cy], -1)
+        e = np.einsum("...i,ij,...j->...", d, np.linalg.inv(cov), d)
+        alpha = np.clip(float(v["a"][0]) * np.exp(-0.5 * e), 0, 1)
+        drawn = rt[..., 3] > 0
+        assert drawn.sum() > 300
+        assert np.abs(rt[..., 3] - alpha)[drawn].max() < 2e-5
+        assert np.abs(rt[..., 1] - alpha * float(v["g"][0]))[drawn].max() < 2e-5
+        # and nothing else was dropped: an undrawn pixel is below the 1/255 discard or outside the +-2 quad of the eigenbasis
+        lam, vec = np.linalg.eigh(cov)
+        qe = np.abs(d @ vec) / np.sqrt(2 * lam)
+        undrawn_ok = (alpha < 1 / 255 + 1e-5) | (qe.max(-1) > 2 - 1e-3)
+        assert undrawn_ok[~drawn].all()
