@@ -257,3 +257,32 @@ def test_anisotropic_splats_match_the_textbook_conic_form(g, O):
         qe = np.abs(d @ vec) / np.sqrt(2 * lam)
         undrawn_ok = (alpha < 1 / 255 + 1e-5) | (qe.max(-1) > 2 - 1e-3)
         assert undrawn_ok[~drawn].all()
+
+
+def test_sh_order3_matches_the_published_real_sh_basis(g, O):
+    """Independent restatement, float64: colour = dc + sum_lm c_lm Y_lm(dir) with the real spherical-harmonic basis of the
+    3DGS paper's eval_sh (constants 0.4886, 1.0925, 0.3154, 0.5463, 0.5900, 2.8906, 0.4570, 0.3732, 1.4453), dir = unit
+    vector from the camera to the splat.  ShadeSH (S/GaussianSplatting.hlsl:139-179) is that sum written per band."""
+    rng = np.random.default_rng(9)
+    cam_pos = np.array([0.3, 0.2, -4.0])
+    cam = camera(g, 320, 240, pos=tuple(cam_pos))
+    for _ in range(5):
+        sh = (0.2 * rng.standard_normal((15, 3))).astype(np.float32)
+        pos = rng.uniform(-0.8, 0.8, 3)
+        asset = one_splat(g, pos=tuple(pos), dc0=(0.9, 1.0, 1.1), sh=sh)
+        s = O.load_splat(asset, 0)
+        d = np.asarray(s["pos"], np.float64) - cam_pos
+        x, y, z = d / np.linalg.norm(d)
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        Y = [-0.4886025119029199 * y, 0.4886025119029199 * z, -0.4886025119029199 * x,
+             1.0925484305920792 * xy, -1.0925484305920792 * yz, 0.31539156525252005 * (2 * zz - xx - yy), -1.0925484305920792 * xz,
+             0.5462742152960396 * (xx - yy),
+             -0.5900435899266435 * y * (3 * xx - yy), 2.890611442640554 * xy * z, -0.4570457994644658 * y * (4 * zz - xx - yy),
+             0.3731763325901154 * z * (2 * zz - 3 * xx - 3 * yy), -0.4570457994644658 * x * (4 * zz - xx - yy),
+             1.445305721320277 * z * (xx - yy), -0.5900435899266435 * x * (xx - 3 * yy)]
+        coeff = np.asarray(s["sh"], np.float64).reshape(15, 3)
+        for order, nterms in ((1, 3), (2, 8), (3, 15)):
+            want = np.maximum(np.asarray(s["col"], np.float64) + sum(Y[k] * coeff[k] for k in range(nterms)), 0.0)
+            v, _ = _view(g, O, asset, cam, sh_order=order)
+            got = np.array([v["r"][0], v["g"][0], v["b"][0]], np.float64)
+            assert np.allclose(got, want, rtol=1.5e-3, atol=2e-4), (order, got, want)     # the result is stored as half
