@@ -71,6 +71,12 @@ GSA_API int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity
  * Returns the number of vertices written, < 0 on I/O error. */
 GSA_API int64_t gsa_ply_write(const char *path, const float *records, uint32_t n, const uint32_t *deleted_bits);
 
+/* "Bake transform" of an export (the _ExportTransformFlags branch of CSExportData, S/SplatUtilities.compute:626-643), as a
+ * host pass over gs_export_splats' records (n x 62 raw attribute values, in place): position by `o2w` (column-major 4x4 =
+ * tr.localToWorldMatrix), orientation by `rot_xyzw` (tr.localRotation; axis flips for negative scale as in the
+ * reference), log-scale by |scale| (tr.localScale), SH bands 1..3 rotated by o2w's normalised 3x3 (CalcSHRotMatrix). */
+GSA_API int gsa_bake_transform(float *records, uint32_t n, const float o2w[16], const float rot_xyzw[4], const float scale[3]);
+
 /* Niantic/Scaniverse .spz input (gzip stream, version 2; E/Utils/SPZFileReader.cs:20-195): same contract as the
  * ply pair above.  Unlike PLY the records need no LinearizeData pass: the unpack already yields linear values. */
 GSA_API int64_t gsa_spz_vertex_count(const char *path);

@@ -211,8 +211,8 @@ GS_API int gs_sort_pairs_host(GsContext *ctx, uint32_t *keys, uint32_t *payload,
  * (pos, nor, f_dc, f_rest channel-major, opacity as logit, log scale, rot wxyz -- the InputSplatData layout,
  * E/Utils/GaussianFileReader.cs:17-26).  nor = (1,1,1) marks a splat the cutouts remove (`cutouts` as in GsFrameParams;
  * may be NULL).  gsa_ply_write (gsplat_asset.h) then writes the file ExportPlyFile writes
- * (E/GaussianSplatRendererEditor.cs:394-445).  bake_transform != 0 (rotate SH into world space) is not built:
- * GS_ERR_UNSUPPORTED_FORMAT.  Blocks. */
+ * (E/GaussianSplatRendererEditor.cs:394-445).  The baked variant (bake_transform != 0) is a host pass over these records,
+ * gsa_bake_transform (gsplat_asset.h); the device entry point itself returns GS_ERR_UNSUPPORTED_FORMAT for the flag.  Blocks. */
 GS_API int gs_export_splats(GsContext *ctx, GsAsset *asset, const GsCutout *cutouts, uint32_t cutout_count,
                             uint32_t bake_transform, void *dst);
 

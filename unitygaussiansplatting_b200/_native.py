@@ -133,6 +133,7 @@ ASSET_SYMBOLS = {
     "gsa_f32tof16": (C.c_uint32, [C.c_float]),
     "gsa_kmeans": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p]),
     "gsa_bc7_encode_block": (None, [C.c_void_p, C.c_void_p]),
+    "gsa_bake_transform": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsa_ply_write": (C.c_int64, [C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p]),
 }
 

@@ -78,7 +78,7 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build_asset(force: bool = False) -> Path:
-    srcs = [CSRC / "asset_creator.cpp", CSRC / "asset_cluster_bc7.cpp"]
+    srcs = [CSRC / "asset_creator.cpp", CSRC / "asset_cluster_bc7.cpp", CSRC / "asset_export.cpp"]
     if force or _stale(ASSET_LIB, [*srcs, ROOT / "include" / "gsplat_asset.h"]):
         # -mavx2: the k-means distance loops evaluate 16 candidate means side by side (no FMA: -ffp-contract=off)
         _run([_host_cxx(), "-O3", "-mavx2", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",

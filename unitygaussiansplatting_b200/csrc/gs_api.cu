@@ -699,7 +699,7 @@ int gs_readback_view(GsAsset *as, void *dst) {
 int gs_export_splats(GsContext *ctx, GsAsset *as, const GsCutout *cutouts, uint32_t cutout_count, uint32_t bake_transform, void *dst) {
   if (!ctx || !as || !dst || (cutout_count && !cutouts)) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "null argument");
   if (as->ctx != ctx) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "asset belongs to another context");
-  if (bake_transform) return fail(ctx, GS_ERR_UNSUPPORTED_FORMAT, "export with a baked transform needs the SH rotation (S/SphericalHarmonics.hlsl), which is not built");
+  if (bake_transform) return fail(ctx, GS_ERR_UNSUPPORTED_FORMAT, "the baked export is a host pass over these records: call with bake_transform = 0, then gsa_bake_transform (gsplat_asset.h)");
   GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   GsFrameParams fp;
   memset(&fp, 0, sizeof(fp));

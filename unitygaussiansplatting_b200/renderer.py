@@ -114,6 +114,45 @@ def _inverse_cached(m: np.ndarray) -> np.ndarray:
     return hit
 
 
+def decompose_trs(m):
+    """Rotation (xyzw) and scale of a shear-free T*R*S matrix: what Transform.localRotation / localScale hold in Unity."""
+    m = np.asarray(m, np.float64)[:3, :3]
+    scale = np.linalg.norm(m, axis=0)
+    if not (scale > 0).all():
+        raise ValueError("degenerate transform: a basis vector has zero length")
+    if np.linalg.det(m) < 0:
+        scale[0] = -scale[0]          # a mirrored transform: Unity reports one negative scale component
+    r = m / scale
+    t = np.trace(r)
+    if t > 0:
+        s4 = np.sqrt(t + 1.0) * 2
+        q = [(r[2, 1] - r[1, 2]) / s4, (r[0, 2] - r[2, 0]) / s4, (r[1, 0] - r[0, 1]) / s4, 0.25 * s4]
+    else:
+        i = int(np.argmax(np.diag(r)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s4 = np.sqrt(1.0 + r[i, i] - r[j, j] - r[k, k]) * 2
+        q = [0.0, 0.0, 0.0, (r[k, j] - r[j, k]) / s4]
+        q[i], q[j], q[k] = 0.25 * s4, (r[j, i] + r[i, j]) / s4, (r[k, i] + r[i, k]) / s4
+    return np.asarray(q, np.float32), scale.astype(np.float32)
+
+
+def bake_transform(records: np.ndarray, localToWorld, rotation=None, scale=None) -> np.ndarray:
+    """In place: exported records (n x 62) moved into world space (gsa_bake_transform); rotation / scale default to the
+    decomposition of the matrix."""
+    if not (records.dtype == np.float32 and records.ndim == 2 and records.shape[1] == 62 and records.flags.c_contiguous):
+        raise ValueError("records must be a C-contiguous (n, 62) float32 array")
+    if rotation is None or scale is None:
+        q, s = decompose_trs(localToWorld)
+        rotation = q if rotation is None else rotation
+        scale = s if scale is None else scale
+    m = colmajor(np.asarray(localToWorld, np.float32))
+    q = np.ascontiguousarray(rotation, np.float32)
+    s = np.ascontiguousarray(scale, np.float32)
+    if N.asset_lib().gsa_bake_transform(records.ctypes.data, records.shape[0], m.ctypes.data, q.ctypes.data, s.ctypes.data) != 0:
+        raise ValueError("gsa_bake_transform failed (degenerate matrix?)")
+    return records
+
+
 def cutout_array(cutouts):
     """[(4x4 matrix = cutout worldToLocal * renderer localToWorld, type_and_flags)] -> GsCutout[] (R/GaussianCutout.cs:26-40)."""
     arr = (N.GsCutout * len(cutouts))()
@@ -165,6 +204,8 @@ class GaussianSplatRenderer:
         self.m_SortNthFrame = 1
         self.m_FrameCounter = 0
         self.localToWorldMatrix = np.eye(4, dtype=np.float32)  # transform of the GameObject
+        self.localRotation = None    # xyzw / None = derived from the matrix (tr.localRotation, tr.localScale; export only)
+        self.localScale = None
         self.m_Cutouts = []          # list of (4x4 matrix, type_and_flags)
         self.m_DeletedBits = None    # np.uint32[ceil(N/32)] or None
         self.blend_mode = N.GS_BLEND_FP16_ROP
@@ -260,8 +301,9 @@ class GaussianSplatRenderer:
         out = np.empty((self.splatCount, 62), np.float32)
         arr = cutout_array(self.m_Cutouts) if self.m_Cutouts else None
         count = len(self.m_Cutouts) if self.m_Cutouts else 0
-        N.check(self.context.handle, self._lib.gs_export_splats(self.context.handle, self._asset, arr, count, 1 if bakeTransform else 0,
-                                                                out.ctypes.data))
+        N.check(self.context.handle, self._lib.gs_export_splats(self.context.handle, self._asset, arr, count, 0, out.ctypes.data))
+        if bakeTransform:   # the _ExportTransformFlags branch of CSExportData, run as a host pass (include/gsplat_asset.h)
+            bake_transform(out, self.localToWorldMatrix, self.localRotation, self.localScale)
         return out
 
     def ExportPlyFile(self, path: str, bakeTransform: bool = False) -> int:
