@@ -1,5 +1,6 @@
 /* gs_oracle.c -- CPU ORACLE (test infrastructure; see gs_oracle.h for the contract).
- * PARITY UNPINNED (no reference golden vectors exist for this path).
+ * Pinned against the reference's own shader source compiled for the CPU (oracle/refhlsl/, tests/test_reference_hlsl.py);
+ * the reference ships no golden vectors for this path.  See gs_oracle.h.
  * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared (see oracle/Makefile).
  */
 #define _GNU_SOURCE

@@ -3,14 +3,20 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may link or call this.  The product (unitygaussiansplatting_b200/) never does.
  *
- * PARITY UNPINNED: the reference (aras-p/UnityGaussianSplatting @ 2c6fed37) ships no
- * golden vectors, known-answer tests or fixtures for any boundary of this path (keys,
- * order, SplatViewData, render target) -- its only goldens are six final PNGs that need
- * the INRIA models, which are not in the repo -- and neither its C#
- * (Unity + Burst) nor its HLSL (DXC + a D3D12/Vulkan device) can run in this image.
- * This file is therefore a plain-C restatement of the reference's shaders, function by
- * function, each citing the HLSL it follows; it is sanity-checked by analytic cases and
- * encode->decode round trips (tests/test_oracle_*.py), not by reference outputs.
+ * PINNING: the reference (aras-p/UnityGaussianSplatting @ 2c6fed37) ships no golden
+ * vectors, known-answer tests or fixtures for any boundary of this path -- its only goldens
+ * are six final PNGs that need the INRIA models, which are not in the repo
+ * -- and neither its C# (Unity + Burst) nor its HLSL (DXC + a GPU) runs in this image.
+ * What pins this restatement instead is the reference's shader SOURCE ITSELF: oracle/refhlsl/
+ * compiles package/Shaders/{GaussianSplatting.hlsl, SplatUtilities.compute, SphericalHarmonics.hlsl,
+ * RenderGaussianSplats.shader} where they lie, with g++, against a C++ shim of HLSL's types and
+ * intrinsics (oracle/_ref/libref_hlsl.so), and tests/test_reference_hlsl.py compares this file
+ * with it stage by stage: sort keys, LoadSplatData + CSCalcViewData, vert + frag, CSExportData
+ * incl. RotateSH -- agreement to float rounding (the two evaluate the same formulas under
+ * different but equally valid contraction / evaluation orders).  NOT covered by that pin:
+ * the fixed-function parts (which pixels a quad covers, the RGBA16F blend), the sort's
+ * tie semantics, and UnityCG's GammaToLinearSpace (third party, not in the reference repo);
+ * those rest on analytic checks and the published formulas (tests/test_oracle_*.py).
  *
  * Arithmetic contract (shared by design with the CUDA path so both can be compared
  * bit-for-bit; HLSL leaves all of this to the driver compiler, so nothing here is pinned

@@ -1,12 +1,13 @@
 """ctypes binding of the CPU oracle (oracle/libgs_oracle.so).  TEST INFRASTRUCTURE ONLY.
 
 May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs.  Never by the product package.  PARITY UNPINNED -- see gs_oracle.h.
+legs.  Never by the product package.  Pinning: see gs_oracle.h (the reference's own shader source compiled for the CPU, oracle/refhlsl/).
 """
 from __future__ import annotations
 
 import ctypes as C
 import subprocess
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -171,3 +172,71 @@ def frame(asset, fp, prev_order=None, width=None, height=None, blend_mode: int =
     W, H = int(width or fp.screen_w), int(height or fp.screen_h)
     rt = render(view, order, W, H, blend_mode, threads)
     return {"keys": keys, "order": order, "view": view, "rt": rt}
+
+
+# ---- oracle/_ref/libref_hlsl.so: the reference's OWN shader source compiled for the CPU (oracle/refhlsl/) ----------------
+REF_HLSL_LIB = HERE / "_ref" / "libref_hlsl.so"
+_ref_hlsl = None
+
+
+def ref_hlsl():
+    """Loads (building first when /root/reference is present) the compiled-reference library; None when neither exists."""
+    global _ref_hlsl
+    if _ref_hlsl is None:
+        if Path("/root/reference/package/Shaders").exists():
+            subprocess.run([sys.executable, str(HERE / "refhlsl" / "build_ref_hlsl.py")], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        if not REF_HLSL_LIB.exists():
+            return None
+        L = C.CDLL(str(REF_HLSL_LIB))
+        L.refhlsl_calc_distances.restype, L.refhlsl_calc_distances.argtypes = C.c_int, [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_void_p, C.c_void_p]
+        L.refhlsl_calc_view.restype, L.refhlsl_calc_view.argtypes = C.c_int, [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_void_p]
+        L.refhlsl_export.restype = C.c_int
+        L.refhlsl_export.argtypes = [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refhlsl_vert.restype, L.refhlsl_vert.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refhlsl_frag.restype, L.refhlsl_frag.argtypes = C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        _ref_hlsl = L
+    return _ref_hlsl
+
+
+def ref_calc_distances(asset, fp, order: np.ndarray) -> np.ndarray:
+    a, f = asset_struct(asset), frame_struct(fp)
+    order = np.ascontiguousarray(order, np.uint32)
+    keys = np.zeros(asset.splatCount, np.uint32)
+    if ref_hlsl().refhlsl_calc_distances(C.byref(a), C.byref(f), order.ctypes.data, keys.ctypes.data) != 0:
+        raise ValueError("compiled reference: unsupported asset format")
+    return keys
+
+
+def ref_calc_view(asset, fp) -> np.ndarray:
+    a, f = asset_struct(asset), frame_struct(fp)
+    view = np.zeros((asset.splatCount, 10), np.uint32)
+    if ref_hlsl().refhlsl_calc_view(C.byref(a), C.byref(f), view.ctypes.data) != 0:
+        raise ValueError("compiled reference: unsupported asset format")
+    return view
+
+
+def ref_export(asset, fp, bake=False, rotation=None, scale=None) -> np.ndarray:
+    a, f = asset_struct(asset), frame_struct(fp)
+    out = np.zeros((asset.splatCount, 62), np.float32)
+    q = np.ascontiguousarray(rotation if rotation is not None else [0, 0, 0, 1], np.float32)
+    s = np.ascontiguousarray(scale if scale is not None else [1, 1, 1], np.float32)
+    if ref_hlsl().refhlsl_export(C.byref(a), C.byref(f), 1 if bake else 0, q.ctypes.data, s.ctypes.data, out.ctypes.data) != 0:
+        raise ValueError("compiled reference: unsupported asset format")
+    return out
+
+
+def ref_vert(view: np.ndarray, order: np.ndarray, inst: int, width: float, height: float):
+    """RenderGaussianSplats.shader vert for the four quad corners of draw instance `inst`: (clip[4,4], quadpos[4,2], colour[4])."""
+    view = np.ascontiguousarray(view, np.uint32)
+    order = np.ascontiguousarray(order, np.uint32)
+    clip, pos, col = np.zeros((4, 4), np.float32), np.zeros((4, 2), np.float32), np.zeros(4, np.float32)
+    ref_hlsl().refhlsl_vert(view.ctypes.data, order.ctypes.data, inst, width, height, clip.ctypes.data, pos.ctypes.data, col.ctypes.data)
+    return clip, pos, col
+
+
+def ref_frag(col, pos_x: float, pos_y: float):
+    """RenderGaussianSplats.shader frag on given interpolants: (rgba, discarded)."""
+    col = np.ascontiguousarray(col, np.float32)
+    out = np.zeros(4, np.float32)
+    d = ref_hlsl().refhlsl_frag(col.ctypes.data, pos_x, pos_y, out.ctypes.data)
+    return out, bool(d)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Regenerates tests/golden/*.npz: outputs of the CPU oracle on two small seeded scenes.
 
-The reference ships no golden vectors for this path (parity unpinned) and cannot run
+The reference ships no golden vectors for this path and cannot run
 here, so these fixtures pin the ORACLE (and the packer) against silent drift, and give the GPU
 tests a file to compare against that does not depend on the oracle being rebuilt on the GPU box.
 Run from the repo root:  python tests/golden/make_golden.py

@@ -1,5 +1,5 @@
 """Analytic sanity checks of the CPU oracle (it is the parity pin, so it gets its own checks;
-SURVEY.md 8c: 'parity unpinned' by the reference's own tests)."""
+SURVEY.md 8c: the reference's own tests pin nothing here; tests/test_reference_hlsl.py adds the compiled shader source)."""
 import numpy as np
 import pytest
 

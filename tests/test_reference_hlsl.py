@@ -1,0 +1,136 @@
+"""The oracle against THE REFERENCE'S OWN SHADER CODE.
+
+oracle/_ref/libref_hlsl.so is package/Shaders/{GaussianSplatting.hlsl, SplatUtilities.compute, SphericalHarmonics.hlsl,
+RenderGaussianSplats.shader} themselves -- read from /root/reference, syntactically rewritten to C++ spelling and compiled with
+g++ against a shim of HLSL's types and intrinsics (oracle/refhlsl/).  Expressions, constants, operation order and branches
+are the reference's; scalar arithmetic is IEEE float32 without contraction.  The oracle (and the CUDA path, bit-identical to
+it) evaluates the same formulas under its own arithmetic contract (explicit fmaf chains, reciprocal constants), so the two
+agree to float rounding, not to the bit: tolerances below are a few ulp, scaled by conditioning where a formula cancels."""
+import numpy as np
+import pytest
+
+from util import camera, one_splat, view_fields
+
+
+@pytest.fixture(scope="module")
+def R(O):
+    if O.ref_hlsl() is None:
+        pytest.skip("oracle/_ref/libref_hlsl.so not built and /root/reference not present")
+    return O
+
+
+def _unsortable(keys):
+    k = keys.astype(np.uint32)
+    u = np.where(k & 0x80000000, k ^ np.uint32(0x80000000), ~k).astype(np.uint32)
+    return u.view(np.float32)
+
+
+def _cov(v):
+    a1, a2 = v["axis1"].astype(np.float64), v["axis2"].astype(np.float64)
+    return 0.5 * (a1[:, :, None] * a1[:, None, :] + a2[:, :, None] * a2[:, None, :])
+
+
+@pytest.mark.parametrize("quality", ["Medium", "VeryHigh", "High", "Low"])
+def test_view_data_matches_the_reference_shader_code(g, R, quality):
+    n = 20000
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, n, 0x5EED0091, quality)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = np.array([[0.8, -0.6, 0.0], [0.6, 0.8, 0.0], [0.0, 0.0, 1.0]], np.float32) * 1.1
+    T[:3, 3] = (0.3, -0.1, 0.2)
+    box = np.diag([1 / 9.0, 1 / 9.0, 1 / 9.0, 1.0]).astype(np.float32)
+    deleted = np.zeros((n + 31) // 32, np.uint32)
+    deleted[3] = 0xF0F0F0F0
+    fp, _keep = g.make_frame_params(camera(g, 320, 240), localToWorld=T, splat_scale=0.9, opacity_scale=1.3, sh_order=3,
+                                    cutouts=[(box, 1)], deleted_bits=deleted, splat_count=n)
+    ref, ora = view_fields(R.ref_calc_view(asset, fp)), view_fields(R.calc_view(asset, fp))
+    # which splats are culled (w = 0: deleted / cut) or behind the camera is decided identically
+    assert np.array_equal(ref["pos"][:, 3] <= 0, ora["pos"][:, 3] <= 0)
+    assert ((ref["pos"][:, 3] == 0) & (ora["pos"][:, 3] == 0)).sum() > 100
+    assert (np.abs(ref["pos"] - ora["pos"]).max(1) <= 2e-6 * (1 + np.abs(ora["pos"]).max(1))).all()
+    vis = ora["pos"][:, 3] > 0
+    for ch in "rgb":                                         # half-precision results: at most one unit in the last place apart
+        d = np.abs(ref[ch][vis] - ora[ch][vis])
+        assert (d <= np.maximum(np.abs(ora[ch][vis]), 2.0 ** -14) * 2.0 ** -9).all(), ch     # <= 2 half ulps
+        assert (d == 0).mean() > 0.9
+    assert np.array_equal(ref["a"][vis], ora["a"][vis])
+    # the two screen axes, through the covariance they encode (eigenvectors of near-circular footprints are ill-defined)
+    cr, co = _cov(ref)[vis], _cov(ora)[vis]
+    rel = np.abs(cr - co).reshape(-1, 4).max(1) / (co[:, 0, 0] + co[:, 1, 1])
+    assert np.percentile(rel, 50) < 1e-6 and np.percentile(rel, 99) < 2e-5 and rel.max() < 2e-3
+
+
+@pytest.mark.parametrize("quality", ["Medium", "VeryHigh"])
+def test_sort_keys_match_the_reference_shader_code(g, R, quality):
+    n = 30000
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, n, 0x5EED0092, quality)
+    fp, _keep = g.make_frame_params(camera(g, 320, 240))
+    order = np.random.default_rng(1).permutation(n).astype(np.uint32)
+    kr, ko = R.ref_calc_distances(asset, fp, order), R.calc_distances(asset, fp, order)
+    zr, zo = _unsortable(kr), _unsortable(ko)
+    assert np.abs(zr - zo).max() <= 4e-6 and (kr == ko).mean() > 0.5     # view-space depth of +-36: a couple of ulp
+    assert np.array_equal(np.argsort(kr, kind="stable")[:100], np.argsort(ko, kind="stable")[:100]) or (kr == ko).mean() < 1.0
+
+
+def test_export_and_baked_transform_match_the_reference_shader_code(g, R):
+    """CSExportData incl. the _ExportTransformFlags branch: QuatMul, scale, and RotateSH (the closed form after sh-lib,
+    S/SphericalHarmonics.hlsl) against the oracle's export and the product's gsa_bake_transform (least-squares band matrices)."""
+    from unitygaussiansplatting_b200.renderer import bake_transform, decompose_trs
+    n = 3000
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, n, 0x5EED0093, "VeryHigh")
+    fp, _keep = g.make_frame_params(camera(g, 64, 64))
+    plain_ref, plain_ora = R.ref_export(asset, fp), R.export_data(asset, fp)
+    assert np.allclose(plain_ref, plain_ora, rtol=2e-6, atol=2e-6)
+    ang = np.radians(50.0)
+    Rm = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]) @ \
+        np.array([[1, 0, 0], [0, np.cos(0.4), -np.sin(0.4)], [0, np.sin(0.4), np.cos(0.4)]])
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = (Rm * 1.25).astype(np.float32)
+    T[:3, 3] = (0.5, 0.25, -0.75)
+    q, s = decompose_trs(T)
+    fpT, _k2 = g.make_frame_params(camera(g, 64, 64), localToWorld=T)
+    baked_ref = R.ref_export(asset, fpT, bake=True, rotation=q, scale=s)
+    baked_ours = bake_transform(R.export_data(asset, fp), T, rotation=q, scale=s)
+    assert np.allclose(baked_ref[:, 0:3], baked_ours[:, 0:3], atol=1e-5)                  # positions
+    assert np.allclose(baked_ref[:, 55:58], baked_ours[:, 55:58], atol=1e-5)              # log scale
+    same = np.abs(baked_ref[:, 58:62] - baked_ours[:, 58:62]).max(1)
+    flip = np.abs(baked_ref[:, 58:62] + baked_ours[:, 58:62]).max(1)
+    assert np.minimum(same, flip).max() < 1e-5                                            # rotation (q and -q are the same)
+    assert np.array_equal(baked_ref[:, 6:9], baked_ours[:, 6:9])                          # band 0
+    assert np.abs(baked_ref[:, 9:54] - plain_ref[:, 9:54]).max() > 0.05                   # the rotation does something ...
+    assert np.abs(baked_ref[:, 9:54] - baked_ours[:, 9:54]).max() < 2e-5                  # ... and ours is the same rotation
+
+
+def test_draw_stages_match_the_reference_shader_code(g, R):
+    """vert + frag of RenderGaussianSplats.shader on one rotated, anisotropic splat: the quad the reference emits maps pixel
+    centres to quad coordinates (the rasteriser's linear interpolation), frag gives the fragment; the oracle's render of that
+    splat (fp32 blend, so the image IS the fragment) must be the same picture."""
+    W, H = 200, 150
+    cam = camera(g, W, H, fov=50.0, pos=(0.1, 0.0, -3.0))
+    asset = one_splat(g, pos=(0.2, -0.1, 0.3), scale=(0.25, 0.08, 0.05), quat=(0.3, 0.5, -0.2, 0.78), opacity=0.65, dc0=(0.7, 0.5, 0.9))
+    fp, _keep = g.make_frame_params(cam, sh_order=0)
+    view = R.calc_view(asset, fp)
+    order = np.arange(1, dtype=np.uint32)
+    rt = R.render(view, order, W, H, blend_mode=1)
+    clip, qpos, col = R.ref_vert(view, order, 0, W, H)
+    assert np.array_equal(np.abs(qpos), np.full((4, 2), 2.0, np.float32))                 # quad corners at +-2 (:54-55)
+    # pixel position of each corner; interpolation inside a parallelogram is affine: solve quad coords from three corners
+    px = np.stack([(clip[:, 0] / clip[:, 3] * 0.5 + 0.5) * W, (0.5 - 0.5 * clip[:, 1] / clip[:, 3]) * H], 1).astype(np.float64)
+    A = np.linalg.solve(np.column_stack([px[:3], np.ones(3)]), qpos[:3].astype(np.float64))   # [x y 1] @ A = q
+    assert np.allclose(np.array([*px[3], 1.0]) @ A, qpos[3], atol=1e-4)
+    checked = drawn = 0
+    for y in range(0, H):
+        for x in range(0, W):
+            qx, qy = np.array([x + 0.5, y + 0.5, 1.0]) @ A
+            if abs(qx) > 2.3 or abs(qy) > 2.3:
+                assert rt[y, x, 3] == 0
+                continue
+            edge = min(abs(abs(qx) - 2), abs(abs(qy) - 2)) < 2e-3
+            out, discarded = R.ref_frag(col, float(qx), float(qy))
+            inside = abs(qx) <= 2 and abs(qy) <= 2
+            want = np.zeros(4, np.float32) if (discarded or not inside) else out
+            if edge or abs(float(np.exp(-(qx * qx + qy * qy))) * col[3] - 1 / 255) < 2e-5:
+                continue                                                                   # on the quad edge / discard threshold
+            assert np.abs(rt[y, x] - want).max() < 3e-6, (x, y, rt[y, x], want)
+            checked += 1
+            drawn += int(want[3] > 0)
+    assert checked > 700 and drawn > 400
