@@ -30,10 +30,15 @@ def _cov(v):
     return 0.5 * (a1[:, :, None] * a1[:, None, :] + a2[:, :, None] * a2[:, None, :])
 
 
-@pytest.mark.parametrize("quality", ["Medium", "VeryHigh", "High", "Low"])
+@pytest.mark.parametrize("quality", ["Medium", "VeryHigh", "High", "Low", "custom-f16sh", "custom-norm6pos"])
 def test_view_data_matches_the_reference_shader_code(g, R, quality):
     n = 20000
-    asset = g.synthetic_asset(g.SCENE_CLUSTERED, n, 0x5EED0091, quality)
+    if quality.startswith("custom"):     # format combinations no preset uses: Float16 SH, Norm6 positions, Norm16 scale
+        fmts = {"custom-f16sh": (g.VectorFormat.Norm16, g.VectorFormat.Norm6, g.ColorFormat.Float16x4, g.SHFormat.Float16),
+                "custom-norm6pos": (g.VectorFormat.Norm6, g.VectorFormat.Norm16, g.ColorFormat.Float32x4, g.SHFormat.Norm11)}[quality]
+        asset = g.create_asset(g.generate_input_splats(g.SCENE_CLUSTERED, n, 0x5EED0091), formats=fmts)
+    else:
+        asset = g.synthetic_asset(g.SCENE_CLUSTERED, n, 0x5EED0091, quality)
     T = np.eye(4, dtype=np.float32)
     T[:3, :3] = np.array([[0.8, -0.6, 0.0], [0.6, 0.8, 0.0], [0.0, 0.0, 1.0]], np.float32) * 1.1
     T[:3, 3] = (0.3, -0.1, 0.2)
