@@ -11,7 +11,8 @@ Recipe (TEST INFRASTRUCTURE; nothing here is product code, nothing of the refere
        - `(Struct)0` -> `Struct()`, `discard;` -> flag + return,
        - of SplatUtilities.compute only the hot-path / export functions are kept (the edit kernels use atomics and
          writable textures the shim does not model);
-  3. write the result to oracle/_ref/ref_cs.inc and ref_ps.inc (git-ignored build outputs) and compile
+  3. write the result to oracle/_ref/ref_cs.inc and ref_ps.inc (intermediates, deleted after a successful build unless
+     --keep is given) and compile
      ref_hlsl_harness.cpp, which includes them together with hlsl_shim.hpp, into oracle/_ref/libref_hlsl.so.
 The GPU box has no /root/reference: it uses the prebuilt library that travels with the tree."""
 from __future__ import annotations
@@ -147,6 +148,10 @@ def main() -> int:
     cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-math-errno", "-fopenmp", "-fPIC", "-shared", "-w",
            "-I", str(HERE), "-I", str(OUT), "-o", str(OUT / "libref_hlsl.so"), str(HERE / "ref_hlsl_harness.cpp")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode == 0 and "--keep" not in sys.argv:
+        # the rewritten reference text is a build intermediate: only the compiled library stays on disk
+        (OUT / "ref_cs.inc").unlink()
+        (OUT / "ref_ps.inc").unlink()
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-6000:])
         return 1
