@@ -194,6 +194,8 @@ def ref_hlsl():
         L.refhlsl_export.argtypes = [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refhlsl_vert.restype, L.refhlsl_vert.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refhlsl_frag.restype, L.refhlsl_frag.argtypes = C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        L.refhlsl_pack_rotation.restype, L.refhlsl_pack_rotation.argtypes = C.c_uint32, [C.c_void_p, C.c_void_p]
+        L.refhlsl_decode_rotation.restype, L.refhlsl_decode_rotation.argtypes = None, [C.c_uint32, C.c_void_p]
         _ref_hlsl = L
     return _ref_hlsl
 

