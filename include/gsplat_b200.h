@@ -128,8 +128,17 @@ typedef struct GsRenderOptions {
   /* Screen-tile partition for multi-GPU: this context composites only
    * 64-pixel rows (GS_BAND_PIXELS, the binning cell) r with (r / band_rows) % partition_count == partition_index.
    * partition_count 0 or 1 = whole image. */
-  uint32_t partition_index, partition_count, band_rows, reserved1;
+  uint32_t partition_index, partition_count, band_rows;
+  uint32_t flags;             /* GsRenderFlags */
 } GsRenderOptions;
+
+typedef enum GsRenderFlags {
+  /* gs_frame with a HOST render target returns as soon as the read-back is ENQUEUED (on a second stream, double-buffered
+   * device staging): frame k's copy overlaps frame k+1's kernels.  The image must be pinned (cudaHostRegister /
+   * cudaMallocHost) and must not be read, nor handed to another frame, until gs_sync (or two later frames) -- the
+   * managed-side analogue is AsyncGPUReadback.  Errors of the frame (e.g. a truncated bin list) surface at gs_sync. */
+  GS_FLAG_ASYNC_READBACK = 1u
+} GsRenderFlags;
 
 /* Per-stage device times of the last gs_frame/gs_sort/gs_calc_view/gs_render call with
  * timing enabled (GaussianSplat.Sort / CalcView / Draw / Compose profiler markers,

@@ -254,3 +254,34 @@ def test_raster_tma_variant_identical(g, O, ctx, tmp_path):
     for k in ("a", "b"):
         assert res["0"][k].any()
         assert np.array_equal(res["0"][k].view(np.uint16), res["1"][k].view(np.uint16))
+
+
+def test_async_readback_equals_blocking(g, ctx):
+    """GS_FLAG_ASYNC_READBACK: host images are filled by a copy stream while the next frame runs; after gs_sync they hold
+    exactly what the blocking path returns, for several frames in rotation over two pinned images."""
+    import torch
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 60000, 0x5EED0081, "Medium")
+    r = g.GaussianSplatRenderer(asset, ctx)
+    cams = [camera(g, 400, 300, pos=(0.2 * k, 0.5, -6.0 + 0.3 * k)) for k in range(5)]
+    want = []
+    for cam in cams:
+        rt = np.zeros((300, 400, 4), np.float16)
+        r.SortAndRenderSplats(cam, rt=rt)
+        want.append(rt)
+    r.ResetOrder()
+    r.m_FrameCounter = 0
+    pins = [torch.zeros((300, 400, 4), dtype=torch.float16).pin_memory() for _ in range(2)]
+    r.async_readback = True
+    got = []
+    for k, cam in enumerate(cams):
+        if k >= 2:
+            ctx.sync()                      # the image about to be reused must have landed: keep a copy of it first
+            got.append(pins[k & 1].numpy().copy())
+        r.SortAndRenderSplats(cam, rt=pins[k & 1].numpy())
+    ctx.sync()
+    # frames 3 and 4 are still in the two images; frames 0..2 were copied out above
+    got.append(pins[1].numpy().copy())      # frame 3
+    got.append(pins[0].numpy().copy())      # frame 4
+    for k in range(5):
+        assert np.array_equal(got[k].view(np.uint16), want[k].view(np.uint16)), "frame %d" % k
+    r.Dispose()

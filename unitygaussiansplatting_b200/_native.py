@@ -59,7 +59,10 @@ class GsImage(C.Structure):
 
 class GsRenderOptions(C.Structure):
     _fields_ = [("blend_mode", C.c_uint32), ("band_packed", C.c_uint32), ("partition_index", C.c_uint32),
-                ("partition_count", C.c_uint32), ("band_rows", C.c_uint32), ("reserved1", C.c_uint32)]
+                ("partition_count", C.c_uint32), ("band_rows", C.c_uint32), ("flags", C.c_uint32)]
+
+
+GS_FLAG_ASYNC_READBACK = 1
 
 
 class GsUnityFrameEvent(C.Structure):   # include/gsplat_b200.h: the payload of CommandBuffer.IssuePluginEventAndData

@@ -43,6 +43,14 @@ struct GsContext {
   size_t rt_bytes = 0;
   void *tgt_scratch = nullptr;
   size_t tgt_bytes = 0;
+  // asynchronous read-back (GS_FLAG_ASYNC_READBACK): two device staging images, a copy stream, and the events that order
+  // "raster k -> copy k" and "copy k -> raster k+2 may reuse the staging image"
+  cudaStream_t copy_stream = nullptr;
+  void *rt_async[2] = {nullptr, nullptr};
+  size_t rt_async_bytes[2] = {0, 0};
+  cudaEvent_t ev_rt_ready[2]{}, ev_copy_done[2]{};
+  bool copy_pending[2] = {false, false};
+  int rt_flip = 0;
   // per-frame optional inputs
   GsCutout *d_cutouts = nullptr;
   uint32_t cutout_cap = 0;
@@ -198,6 +206,17 @@ static float ev_ms(GsContext *ctx, int a, int b) {
   float ms = 0.0f;
   if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0f; }
   return ms;
+}
+
+// GS_FLAG_ASYNC_READBACK plumbing, created on first use
+static int ensure_async_readback(GsContext *ctx) {
+  if (ctx->copy_stream) return GS_OK;
+  GS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    GS_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_rt_ready[i], cudaEventDisableTiming));
+    GS_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_done[i], cudaEventDisableTiming));
+  }
+  return GS_OK;
 }
 
 static uint32_t pix_bytes(uint32_t fmt) { return fmt == GS_PIX_RGBA16F ? 8u : 16u; }
@@ -383,6 +402,12 @@ void gs_destroy(GsContext *ctx) {
   cudaFree(ctx->sort.ghist); cudaFree(ctx->sort.tickets); cudaFree(ctx->d_scalar);
   cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
   cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ctx->rt_async[i]);
+    if (ctx->ev_rt_ready[i]) cudaEventDestroy(ctx->ev_rt_ready[i]);
+    if (ctx->ev_copy_done[i]) cudaEventDestroy(ctx->ev_copy_done[i]);
+  }
   for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -392,7 +417,12 @@ int gs_sync(GsContext *ctx) {
   if (!ctx) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "null context");
   GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   // frames rendered into device images are not checked when they are enqueued: surface a truncated bin list here
-  return check_bin_overflow(ctx);
+  const int rc = check_bin_overflow(ctx);
+  if (ctx->copy_stream) {   // asynchronous read-backs in flight complete here
+    GS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    ctx->copy_pending[0] = ctx->copy_pending[1] = false;
+  }
+  return rc;
 }
 
 int gs_set_timing(GsContext *ctx, int enabled) {
@@ -601,8 +631,21 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
   void *d_rt;
   uint32_t d_pitch;
   const bool rt_dev = rt && rt->memory == GS_MEM_DEVICE;
+  const bool async_rb = rt && !rt_dev && !tgt && (opt.flags & GS_FLAG_ASYNC_READBACK) != 0;
+  int slot = 0;
   if (rt_dev) { d_rt = rt->data; d_pitch = rt_pitch; }
-  else {
+  else if (async_rb) {
+    if ((rc = ensure_async_readback(ctx))) return rc;
+    slot = ctx->rt_flip;
+    ctx->rt_flip ^= 1;
+    d_pitch = W * pix_bytes(rt_fmt);
+    // the staging image of two frames ago: its copy must have left the device before this frame's raster overwrites it
+    if (ctx->copy_pending[slot]) GS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[slot], 0));
+    if (ctx->rt_async_bytes[slot] < (size_t)d_pitch * H && ctx->copy_pending[slot]) GS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));  // about to be freed
+    if ((rc = grow(ctx, &ctx->rt_async[slot], &ctx->rt_async_bytes[slot], (size_t)d_pitch * H))) return rc;
+    d_rt = ctx->rt_async[slot];
+    if (opt.partition_count > 1) GS_CUDA_TRY(ctx, cudaMemsetAsync(d_rt, 0, (size_t)d_pitch * H, ctx->stream));
+  } else {
     d_pitch = W * pix_bytes(rt_fmt);
     if ((rc = grow(ctx, &ctx->rt_scratch, &ctx->rt_bytes, (size_t)d_pitch * H))) return rc;
     d_rt = ctx->rt_scratch;
@@ -610,6 +653,14 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
   }
   if ((rc = do_render(ctx, as, fc, opt, d_rt, d_pitch, rt_fmt))) return rc;
   bool synced = false;
+  if (async_rb) {
+    GS_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_rt_ready[slot], ctx->stream));
+    GS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rt_ready[slot], 0));
+    GS_CUDA_TRY(ctx, cudaMemcpy2DAsync(rt->data, rt_pitch, d_rt, d_pitch, (size_t)W * pix_bytes(rt_fmt), H, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    GS_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy_done[slot], ctx->copy_stream));
+    ctx->copy_pending[slot] = true;
+    return GS_OK;   // completion and the bin-list check: gs_sync
+  }
   if (rt && !rt_dev) {
     GS_CUDA_TRY(ctx, cudaMemcpy2DAsync(rt->data, rt_pitch, d_rt, d_pitch, (size_t)W * pix_bytes(rt_fmt), H, cudaMemcpyDeviceToHost, ctx->stream));
   }

@@ -215,6 +215,7 @@ k_onesweep(const uint32_t *__restrict__ src_k, const uint32_t *__restrict__ src_
       *lb = kFlagIncl | (prefix + pub);
     }
   }
+  __syncwarp();   // the spin loop above ends per thread: tell the compiler the warp is whole again before the ballots
   GS_TRACE(2);
   if (!GATHER) {  // payloads: issued now, consumed at the scatter
     if (full_tile) {
@@ -236,16 +237,14 @@ k_onesweep(const uint32_t *__restrict__ src_k, const uint32_t *__restrict__ src_
   for (int i = 0; i < kSortKPT; ++i) {
     const uint32_t d = (key[i] >> shift) & (NB - 1);
     const uint32_t m = match_digit<BITS>(d);
-    const uint32_t leader = __ffs(m) - 1;
-    uint32_t prev = 0;
-    if (lane == leader) {
-      prev = s_whist[warp][d];
-      s_whist[warp][d] = prev + __popc(m);
-    }
-    prev = __shfl_sync(0xffffffffu, prev, leader);
-    const uint32_t r = prev + __popc(m & lt_mask);
+    // every lane reads its digit's running count (lanes of one digit read one word: a broadcast), then the lowest lane of
+    // each digit group -- the one with no equal-digit lane below it -- stores the new count: a predicated store, no
+    // branch, no shuffle.  Shared-memory accesses of one warp execute in program order, so round i+1 sees round i's store.
+    const uint32_t below = __popc(m & lt_mask);
+    const uint32_t prev = s_whist[warp][d];
+    if (below == 0) s_whist[warp][d] = prev + __popc(m);
+    const uint32_t r = prev + below;
     if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
-    __syncwarp();
   }
   __syncthreads();
   GS_TRACE(3);

@@ -211,6 +211,7 @@ class GaussianSplatRenderer:
         self.blend_mode = N.GS_BLEND_FP16_ROP
         self.partition = (0, 0, 1)   # index, count, band_rows
         self.band_packed = False
+        self.async_readback = False  # host render targets are filled asynchronously (pinned memory; context.sync() completes them)
         d = asset.desc()
         h = C.c_void_p()
         N.check(self.context.handle, self._lib.gs_asset_upload(self.context.handle, C.byref(d), C.byref(h)))
@@ -247,6 +248,7 @@ class GaussianSplatRenderer:
         o.blend_mode = self.blend_mode
         o.partition_index, o.partition_count, o.band_rows = self.partition
         o.band_packed = 1 if self.band_packed else 0
+        o.flags = N.GS_FLAG_ASYNC_READBACK if self.async_readback else 0
         return o
 
     # -- the hot path ----------------------------------------------------------------------------
