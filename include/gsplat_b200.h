@@ -119,6 +119,7 @@ typedef struct GsImage {
 typedef enum GsBlendMode { GS_BLEND_FP16_ROP = 0, GS_BLEND_FP32 = 1 } GsBlendMode;
 
 #define GS_BAND_PIXELS 64u /* height of one partition row = edge of a binning cell (csrc/gs_common.cuh kBin) */
+#define GS_TILE_PIXELS 16u /* edge of a raster tile = granularity of row_begin/row_end (csrc/gs_common.cuh kTile) */
 
 typedef struct GsRenderOptions {
   uint32_t blend_mode;        /* GsBlendMode */
@@ -130,6 +131,10 @@ typedef struct GsRenderOptions {
    * partition_count 0 or 1 = whole image. */
   uint32_t partition_index, partition_count, band_rows;
   uint32_t flags;             /* GsRenderFlags */
+  /* Contiguous partition (what gs_group_frame uses): when row_end > row_begin this context composites only the 16-pixel
+   * raster-tile rows [row_begin, row_end) (GS_TILE_PIXELS), straight into their natural place of a full-size target;
+   * partition_* and band_packed are then ignored.  0,0 = not used. */
+  uint32_t row_begin, row_end;
 } GsRenderOptions;
 
 typedef enum GsRenderFlags {
@@ -137,7 +142,12 @@ typedef enum GsRenderFlags {
    * device staging): frame k's copy overlaps frame k+1's kernels.  The image must be pinned (cudaHostRegister /
    * cudaMallocHost) and must not be read, nor handed to another frame, until gs_sync (or two later frames) -- the
    * managed-side analogue is AsyncGPUReadback.  Errors of the frame (e.g. a truncated bin list) surface at gs_sync. */
-  GS_FLAG_ASYNC_READBACK = 1u
+  GS_FLAG_ASYNC_READBACK = 1u,
+  /* Do not start from a cleared target: read `rt` and blend this asset UNDER what is already there.  The reference
+   * clears _GaussianSplatRT once per camera (R/GaussianSplatRenderer.cs:196) and then draws every active splat object
+   * into it, nearest object first (GatherSplatsForCamera :73-105, loop :111-168): render the first object without this
+   * flag and each further one with it.  A host `rt` is uploaded first. */
+  GS_FLAG_LOAD_RT = 2u
 } GsRenderFlags;
 
 /* Per-stage device times of the last gs_frame/gs_sort/gs_calc_view/gs_render call with
@@ -207,6 +217,56 @@ GS_API int gs_frame(GsContext *ctx, GsAsset *asset, const GsFrameParams *fp,
  * image (device or host) in normal row order. */
 GS_API int gs_unshuffle_bands(GsContext *ctx, const void *gathered, uint32_t partition_count, uint32_t band_rows,
                               uint32_t rows_per_partition, uint32_t pixel_format, GsImage *out);
+
+/* ---- several GPUs of one box (the reference itself is single-GPU) ----------------------------------
+ * A group renders ONE frame on G GPUs and leaves, on every GPU, exactly what gs_frame leaves on one: the same draw order
+ * (bit for bit: the persistent _SplatSortKeys contract of R/GpuSorting.cs:142-198 seeded by last frame's order,
+ * R/GaussianSplatRenderer.cs:612-639) and the same render target.  Per frame and GPU:
+ *   - the depth sort is sharded by KEY RANGE: every GPU computes the (cheap) key table, takes the splats whose key lies
+ *     between two shared splitters -- in last frame's order, so ties keep the reference's order -- sorts only those, and one
+ *     NCCL exchange of the id slabs gives every GPU the whole order;
+ *   - view-calc, binning and compositing are sharded by SCREEN ROWS: a contiguous range of 16-pixel rows per GPU
+ *     (GsRenderOptions.row_begin/row_end), rebalanced every frame from the measured per-row cost, composited straight
+ *     into place, then one NCCL exchange of the row ranges ("a single all-gather of the composited tile buffers").
+ * Two ways to form a group:
+ *   gs_group_join    one process per GPU (torchrun-style): every process passes its own context, the group size, its rank
+ *                    and the 128-byte id rank 0 got from gs_group_unique_id (sent over any host channel);
+ *   gs_group_create  one process driving n GPUs (what a Unity host would do): the library creates the n contexts.
+ *                    GS_GROUP_EMULATE lets device indices repeat: the "GPUs" are then n contexts on the same device and the
+ *                    exchanges are device-to-device copies -- the whole sharded path on a single-GPU box, for tests.
+ * NCCL is bound at run time (libnccl.so.2; a copy already loaded into the process, e.g. PyTorch's, is reused). */
+typedef struct GsGroup GsGroup;
+#define GS_GROUP_ID_BYTES 128u
+#define GS_GROUP_MAX_GPUS 16u
+typedef enum GsGroupFlags { GS_GROUP_EMULATE = 1u } GsGroupFlags;
+
+typedef struct GsGroupStats {      /* of the first local member, last gs_group_frame with timing enabled (gs_set_timing) */
+  float distances_ms, slab_sort_ms, order_exchange_ms, view_ms, bin_ms, raster_ms, image_exchange_ms, total_ms;
+  uint32_t group_size, rank;
+  uint32_t row_bounds[GS_GROUP_MAX_GPUS + 1];   /* 16-pixel row ranges of this frame: GPU g composites [row_bounds[g], row_bounds[g+1]) */
+  uint32_t slab_counts[GS_GROUP_MAX_GPUS];      /* splats each GPU sorted this frame */
+} GsGroupStats;
+
+GS_API int gs_group_unique_id(void *id_out /* GS_GROUP_ID_BYTES */);
+GS_API int gs_group_join(GsContext *ctx, uint32_t group_size, uint32_t rank, const void *id, GsGroup **out);
+GS_API int gs_group_create(const int *cuda_devices, uint32_t n, uint32_t flags, GsGroup **out);
+GS_API void gs_group_destroy(GsGroup *group);
+GS_API uint32_t gs_group_size(const GsGroup *group);
+GS_API uint32_t gs_group_local_count(const GsGroup *group);          /* members driven by this process: 1 after join, n after create */
+GS_API GsContext *gs_group_context(GsGroup *group, uint32_t local_index);
+/* CreateResourcesForAsset on every local member (R/GaussianSplatRenderer.cs:373-445): assets_out[local_count]. */
+GS_API int gs_group_asset_upload(GsGroup *group, const GsAssetDesc *desc, GsAsset **assets_out);
+/* SortAndRenderSplats (R/GaussianSplatRenderer.cs:108-169) on the group.  assets[i] / rts[i] belong to local member i;
+ * rts[i] is a full-size image (device or host memory; NULL = this member keeps the frame in library scratch only).  Every
+ * non-NULL rts[i] ends up holding the COMPLETE render target.  `opt`: blend_mode only.  Collective: every process of the
+ * group must call it with the same parameters. */
+GS_API int gs_group_frame(GsGroup *group, GsAsset *const *assets, const GsFrameParams *fp, const GsRenderOptions *opt, int do_sort,
+                          GsImage *const *rts);
+GS_API int gs_group_sync(GsGroup *group);
+GS_API int gs_group_get_stats(GsGroup *group, GsGroupStats *out);
+/* The row balancer by itself (host arithmetic, no GPU): splits `rows` 16-pixel rows with the given measured costs into
+ * `parts` contiguous ranges of near-equal cost; bounds_out[parts + 1], bounds_out[0] = 0, bounds_out[parts] = rows. */
+GS_API int gs_group_balance_rows(const uint32_t *row_cost, uint32_t rows, uint32_t parts, uint32_t *bounds_out);
 
 /* ---- stand-alone sorter (GpuSorting.Dispatch, R/GpuSorting.cs:142-198) ----------- */
 /* Stable ascending sort of `count` (uint32 key, uint32 payload) pairs in place in DEVICE

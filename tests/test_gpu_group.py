@@ -1,0 +1,130 @@
+"""The group path (gs_group_*: key-range-sharded sort + row-range-sharded view-calc / binning / compositing) against the
+single-GPU frame: draw order and render target must be BIT-identical on every member, frame after frame, while the camera
+moves (so the order carried from frame to frame, the splitters and the re-cut row ranges are all exercised).
+
+On a one-GPU box the group is emulated (GS_GROUP_EMULATE: G contexts on the same device, exchanges by device copies), which
+runs every kernel and every piece of host logic of the real thing except the NCCL calls themselves; test_group_nccl_*
+needs >= 2 devices and is skipped otherwise (bench.py --gpus N makes the same assertion on the NCCL path)."""
+import numpy as np
+import pytest
+
+from util import camera
+
+pytestmark = pytest.mark.gpu
+
+
+def _cams(g, w, h, k):
+    # a short fly-through: position and heading change every frame
+    out = []
+    for i in range(k):
+        a = 0.12 * i
+        out.append(camera(g, w, h, pos=(0.4 * i - 0.5, 0.5 + 0.05 * i, -6.0 + 0.35 * i), forward=(np.sin(a), -0.02 * i, np.cos(a))))
+    return out
+
+
+def _single_gpu_sequence(g, ctx, asset, cams, sort_nth=1, **knobs):
+    r = g.GaussianSplatRenderer(asset, ctx)
+    r.m_SortNthFrame = sort_nth
+    for k, v in knobs.items():
+        setattr(r, k, v)
+    frames = []
+    for cam in cams:
+        rt = np.zeros((cam.pixelHeight, cam.pixelWidth, 4), np.float16)
+        r.SortAndRenderSplats(cam, rt=rt)
+        frames.append((r.readback_order(), rt))
+    r.Dispose()
+    return frames
+
+
+def _check_group(g, grp, cams, want):
+    for k, cam in enumerate(cams):
+        rts = [np.zeros((cam.pixelHeight, cam.pixelWidth, 4), np.float16) for _ in range(grp.local_count)]
+        grp.SortAndRenderSplats(cam, rts=rts)
+        st = grp.stats()
+        bounds = list(st.row_bounds[: grp.size + 1])
+        assert bounds[0] == 0 and bounds[-1] == (cam.pixelHeight + 15) // 16 and all(b1 >= b0 for b0, b1 in zip(bounds, bounds[1:]))
+        assert sum(st.slab_counts[: grp.size]) == grp.splatCount
+        for i in range(grp.local_count):
+            assert np.array_equal(grp.readback_order(i), want[k][0]), "frame %d member %d: draw order differs from the single-GPU sort" % (k, i)
+            assert rts[i].any()
+            assert np.array_equal(rts[i].view(np.uint16), want[k][1].view(np.uint16)), "frame %d member %d: render target differs" % (k, i)
+
+
+@pytest.mark.parametrize("gpus", [1, 2, 3, 4, 8])
+def test_group_emulated_equals_single_gpu(g, ctx, gpus):
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 150000, 0x5EED0071, "Medium")
+    cams = _cams(g, 640, 400, 5)
+    want = _single_gpu_sequence(g, ctx, asset, cams)
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    grp = GaussianSplatGroup.create(asset, [0] * gpus, emulate=True)
+    _check_group(g, grp, cams, want)
+    grp.close()
+
+
+def test_group_more_gpus_than_rows_and_ties(g, ctx):
+    """A 40-pixel-high screen has 3 rows of 16 pixels for 8 members; the lattice asset is full of depth ties."""
+    asset = g.synthetic_asset(g.SCENE_LATTICE, 1000, 0x5EED0001, "Medium")
+    cams = [camera(g, 96, 40, pos=(0.1 * i, 0.0, -4.0)) for i in range(4)]
+    want = _single_gpu_sequence(g, ctx, asset, cams)
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    grp = GaussianSplatGroup.create(asset, [0] * 8, emulate=True)
+    _check_group(g, grp, cams, want)
+    grp.close()
+
+
+def test_group_sort_every_other_frame_and_knobs(g, ctx):
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 60000, 0x5EED0072, "VeryHigh")
+    cams = _cams(g, 333, 211, 5)
+    knobs = dict(m_SplatScale=1.3, m_OpacityScale=0.8, m_SHOrder=2)
+    want = _single_gpu_sequence(g, ctx, asset, cams, sort_nth=2, **knobs)
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    grp = GaussianSplatGroup.create(asset, [0, 0, 0], emulate=True)
+    grp.m_SortNthFrame = 2
+    for k, v in knobs.items():
+        setattr(grp, k, v)
+    _check_group(g, grp, cams, want)
+    grp.close()
+
+
+def test_group_device_images(g, ctx):
+    """Members may hand in device images (the zero-copy host): the exchange happens in place in them."""
+    import torch
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 80000, 0x5EED0073, "Medium")
+    cams = _cams(g, 512, 320, 3)
+    want = _single_gpu_sequence(g, ctx, asset, cams)
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    grp = GaussianSplatGroup.create(asset, [0, 0, 0, 0], emulate=True)
+    rts = [torch.zeros((320, 512, 4), dtype=torch.float16, device="cuda") for _ in range(4)]
+    for k, cam in enumerate(cams):
+        grp.SortAndRenderSplats(cam, rts=rts)
+        grp.sync()
+        for i in range(4):
+            assert np.array_equal(rts[i].cpu().numpy().view(np.uint16), want[k][1].view(np.uint16)), "frame %d member %d" % (k, i)
+    grp.close()
+
+
+def test_group_full_size_cfg2(g, ctx):
+    """BASELINE configs[1]-sized: 6,131,954 Medium @1200x797 on an emulated group of 4."""
+    import bench
+    _g, asset, cam0 = bench.make_scene()
+    cams = [bench.orbit_camera(k) for k in range(3)]
+    want = _single_gpu_sequence(g, ctx, asset, cams)
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    grp = GaussianSplatGroup.create(asset, [0, 0, 0, 0], emulate=True)
+    _check_group(g, grp, cams, want)
+    grp.close()
+
+
+def test_group_nccl_single_process(g, ctx):
+    """gs_group_create over real devices: NCCL (ncclCommInitAll) inside the library."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    n = min(torch.cuda.device_count(), 4)
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 150000, 0x5EED0071, "Medium")
+    cams = _cams(g, 640, 400, 4)
+    want = _single_gpu_sequence(g, ctx, asset, cams)
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    grp = GaussianSplatGroup.create(asset, list(range(n)))
+    _check_group(g, grp, cams, want)
+    grp.close()

@@ -59,10 +59,23 @@ class GsImage(C.Structure):
 
 class GsRenderOptions(C.Structure):
     _fields_ = [("blend_mode", C.c_uint32), ("band_packed", C.c_uint32), ("partition_index", C.c_uint32),
-                ("partition_count", C.c_uint32), ("band_rows", C.c_uint32), ("flags", C.c_uint32)]
+                ("partition_count", C.c_uint32), ("band_rows", C.c_uint32), ("flags", C.c_uint32),
+                ("row_begin", C.c_uint32), ("row_end", C.c_uint32)]
 
 
 GS_FLAG_ASYNC_READBACK = 1
+GS_FLAG_LOAD_RT = 2
+GS_GROUP_EMULATE = 1
+GS_GROUP_ID_BYTES = 128
+GS_GROUP_MAX_GPUS = 16
+GS_TILE_PIXELS = 16
+
+
+class GsGroupStats(C.Structure):
+    _fields_ = [("distances_ms", C.c_float), ("slab_sort_ms", C.c_float), ("order_exchange_ms", C.c_float), ("view_ms", C.c_float),
+                ("bin_ms", C.c_float), ("raster_ms", C.c_float), ("image_exchange_ms", C.c_float), ("total_ms", C.c_float),
+                ("group_size", C.c_uint32), ("rank", C.c_uint32), ("row_bounds", C.c_uint32 * (GS_GROUP_MAX_GPUS + 1)),
+                ("slab_counts", C.c_uint32 * GS_GROUP_MAX_GPUS)]
 
 
 class GsUnityFrameEvent(C.Structure):   # include/gsplat_b200.h: the payload of CommandBuffer.IssuePluginEventAndData
@@ -107,6 +120,19 @@ NATIVE_SYMBOLS = {
     "gs_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GsFrameParams), C.POINTER(GsRenderOptions), C.c_int,
                            C.POINTER(GsImage), C.POINTER(GsImage)]),
     "gs_unshuffle_bands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(GsImage)]),
+    "gs_group_unique_id": (C.c_int, [C.c_void_p]),
+    "gs_group_join": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gs_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "gs_group_destroy": (None, [C.c_void_p]),
+    "gs_group_size": (C.c_uint32, [C.c_void_p]),
+    "gs_group_local_count": (C.c_uint32, [C.c_void_p]),
+    "gs_group_context": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "gs_group_asset_upload": (C.c_int, [C.c_void_p, C.POINTER(GsAssetDesc), C.POINTER(C.c_void_p)]),
+    "gs_group_frame": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(GsFrameParams), C.POINTER(GsRenderOptions), C.c_int,
+                                 C.POINTER(C.POINTER(GsImage))]),
+    "gs_group_sync": (C.c_int, [C.c_void_p]),
+    "gs_group_get_stats": (C.c_int, [C.c_void_p, C.POINTER(GsGroupStats)]),
+    "gs_group_balance_rows": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "gs_sort_pairs_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "gs_sort_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "gs_readback_order": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -10,66 +10,11 @@
 #include <new>
 #include <string>
 
-#include "gs_kernels.cuh"
+#include "gs_internal.cuh"
 
-struct GsContext;
 namespace gs {
 static thread_local std::string g_last_error;
-int fail(GsContext *ctx, int code, const std::string &msg);
-int fail_cuda(GsContext *ctx, cudaError_t e, const char *expr, const char *file, int line);
 }  // namespace gs
-
-enum { EV_BEGIN = 0, EV_DIST, EV_SORT0, EV_SORT1, EV_SORT2, EV_SORT3, EV_SORT4, EV_VIEW0, EV_VIEW1, EV_BIN1, EV_RASTER1, EV_COMP1, EV_COUNT };
-
-struct GsContext {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  std::string err;
-  bool timing = false;
-  GsStageTimes times{};
-  cudaEvent_t ev[EV_COUNT]{};
-  bool ev_valid[EV_COUNT]{};
-  // sort scratch
-  gs::SortScratch sort{};
-  uint32_t sort_capacity = 0;
-  size_t lookback_words = 0;
-  uint32_t *d_scalar = nullptr;  // small device scalars (standalone sorter count)
-  // bin scratch
-  gs::BinScratch bin{};
-  uint32_t bin_blocks_cap = 0, tiles_cap = 0, raster_tiles_cap = 0, raster_tiles_cur = 0;
-  // image scratch
-  void *rt_scratch = nullptr;
-  size_t rt_bytes = 0;
-  void *tgt_scratch = nullptr;
-  size_t tgt_bytes = 0;
-  // asynchronous read-back (GS_FLAG_ASYNC_READBACK): two device staging images, a copy stream, and the events that order
-  // "raster k -> copy k" and "copy k -> raster k+2 may reuse the staging image"
-  cudaStream_t copy_stream = nullptr;
-  void *rt_async[2] = {nullptr, nullptr};
-  size_t rt_async_bytes[2] = {0, 0};
-  cudaEvent_t ev_rt_ready[2]{}, ev_copy_done[2]{};
-  bool copy_pending[2] = {false, false};
-  int rt_flip = 0;
-  // per-frame optional inputs
-  GsCutout *d_cutouts = nullptr;
-  uint32_t cutout_cap = 0;
-  uint32_t *d_deleted = nullptr;
-  size_t deleted_words = 0;
-  uint32_t launches = 0;
-};
-
-struct GsAsset {
-  GsContext *ctx = nullptr;
-  gs::AssetView av{};
-  void *d_pos = nullptr, *d_other = nullptr, *d_sh = nullptr, *d_color = nullptr, *d_chunks = nullptr;
-  uint32_t *order = nullptr, *keys = nullptr, *key_table = nullptr, *view = nullptr, *rect = nullptr, *d_n = nullptr;
-  float4 *draw = nullptr;  // raster-ready 48-byte records of the drawable splats
-  bool view_valid = false;   // the full 40-byte _SplatViewData buffer is current (gs_calc_view)
-  bool draw_valid = false;   // draw records + bin rects are current (gs_calc_view or gs_frame)
-  uint32_t draw_part[3] = {0, 0, 1};   // the tile partition those records were culled for (count <= 1: complete)
-  uint32_t view_w = 0, view_h = 0;
-};
 
 namespace gs {
 
@@ -95,7 +40,7 @@ static void mat_mul(const float *a, const float *b, float *o) {
 
 // Uniform derivation of CalcViewData (R/GaussianSplatRenderer.cs:586-606) and SortPoints (:617-629),
 // plus the CalcCovariance2D constants that depend only on the camera (S/GaussianSplatting.hlsl:62-70).
-static FrameConsts make_frame_consts(const GsFrameParams *fp) {
+FrameConsts make_frame_consts(const GsFrameParams *fp) {
   FrameConsts fc;
   memset(&fc, 0, sizeof(fc));
   float mv[16], vp[16], w2c[16], mvs[16];
@@ -149,7 +94,7 @@ static int grow(GsContext *ctx, void **p, size_t *cur, size_t need) {
   return GS_OK;
 }
 
-static int ensure_sort_scratch(GsContext *ctx, uint32_t capacity) {
+int ensure_sort_scratch(GsContext *ctx, uint32_t capacity) {
   if (capacity <= ctx->sort_capacity) return GS_OK;
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->sort.alt_keys); cudaFree(ctx->sort.alt_vals); cudaFree(ctx->sort.lookback);
@@ -183,9 +128,12 @@ static int ensure_bin_scratch(GsContext *ctx, uint32_t n, uint32_t tiles, uint32
   const uint32_t blocks = n / 1024 + 2;
   if (blocks > ctx->bin_blocks_cap) {
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->bin.block_sums);
-    ctx->bin.block_sums = nullptr;
+    cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.list_ids); cudaFree(ctx->bin.cmp_status);
+    ctx->bin.block_sums = ctx->bin.list_ids = ctx->bin.cmp_status = nullptr;
+    ctx->bin_blocks_cap = 0;
     GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.block_sums, (size_t)blocks * 4));
+    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.list_ids, (size_t)n * 4 + 16));
+    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.cmp_status, compact_status_words(n) * 4));
     ctx->bin_blocks_cap = blocks;
   }
   if (tiles > ctx->tiles_cap) {
@@ -198,7 +146,7 @@ static int ensure_bin_scratch(GsContext *ctx, uint32_t n, uint32_t tiles, uint32
   return GS_OK;
 }
 
-static void rec(GsContext *ctx, int e) {
+void rec(GsContext *ctx, int e) {
   if (ctx->timing) { cudaEventRecord(ctx->ev[e], ctx->stream); ctx->ev_valid[e] = true; }
 }
 static float ev_ms(GsContext *ctx, int a, int b) {
@@ -219,9 +167,9 @@ static int ensure_async_readback(GsContext *ctx) {
   return GS_OK;
 }
 
-static uint32_t pix_bytes(uint32_t fmt) { return fmt == GS_PIX_RGBA16F ? 8u : 16u; }
+uint32_t pix_bytes(uint32_t fmt) { return fmt == GS_PIX_RGBA16F ? 8u : 16u; }
 
-static int upload_frame_inputs(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
+int upload_frame_inputs(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, cudaStream_t stream) {
   if (fp->cutouts && fp->cutout_count) {
     if (fp->cutout_count > ctx->cutout_cap) {
       cudaStreamSynchronize(ctx->stream);
@@ -230,7 +178,7 @@ static int upload_frame_inputs(GsContext *ctx, GsAsset *as, const GsFrameParams 
       GS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_cutouts, sizeof(GsCutout) * fp->cutout_count));
       ctx->cutout_cap = fp->cutout_count;
     }
-    GS_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cutouts, fp->cutouts, sizeof(GsCutout) * fp->cutout_count, cudaMemcpyHostToDevice, ctx->stream));
+    GS_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cutouts, fp->cutouts, sizeof(GsCutout) * fp->cutout_count, cudaMemcpyHostToDevice, stream));
   }
   if (fp->deleted_bits) {
     size_t words = ((size_t)as->av.n + 31) / 32;
@@ -241,12 +189,12 @@ static int upload_frame_inputs(GsContext *ctx, GsAsset *as, const GsFrameParams 
       GS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_deleted, words * 4));
       ctx->deleted_words = words;
     }
-    GS_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_deleted, fp->deleted_bits, words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    GS_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_deleted, fp->deleted_bits, words * 4, cudaMemcpyHostToDevice, stream));
   }
   return GS_OK;
 }
 
-static int check_params(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
+int check_params(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
   if (!ctx || !as || !fp) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "null context/asset/params");
   if (as->ctx != ctx) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "asset belongs to another context");
   GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));   // the caller's current device may be another one
@@ -278,18 +226,20 @@ static GsRenderOptions default_opts() {
   return o;
 }
 
-static int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameConsts &fc, bool cull, const GsRenderOptions &opt) {
-  int rc = upload_frame_inputs(ctx, as, fp);
+int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameConsts &fc, bool cull, const GsRenderOptions &opt,
+            cudaStream_t stream) {
+  int rc = upload_frame_inputs(ctx, as, fp, stream);
   if (rc) return rc;
-  rec(ctx, EV_VIEW0);
-  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, as->draw, cull, make_partition(opt), ctx->stream);
-  rec(ctx, EV_VIEW1);
+  const bool own = stream == ctx->stream;   // the group path runs view-calc beside the sort on a second stream and times it itself
+  if (own) rec(ctx, EV_VIEW0);
+  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, as->draw, as->draw_mask, cull, make_partition(opt), stream);
+  if (own) rec(ctx, EV_VIEW1);
   ctx->launches += 1;
   as->view_valid = !cull;
   as->draw_valid = true;
   {
     const gs::Partition p = make_partition(opt);
-    as->draw_part[0] = p.index; as->draw_part[1] = cull ? p.count : 0; as->draw_part[2] = p.band;
+    as->draw_part[0] = p.range ? p.t0 : p.index; as->draw_part[1] = cull ? (p.range ? 0xFFFFFFFFu : p.count) : 0; as->draw_part[2] = p.range ? p.t1 : p.band;
   }
   as->view_w = (uint32_t)fp->screen_w;
   as->view_h = (uint32_t)fp->screen_h;
@@ -298,13 +248,14 @@ static int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const F
 }
 
 // binning + raster into a device image
-static int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const GsRenderOptions &opt, void *d_rt, uint32_t pitch,
+int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const GsRenderOptions &opt, void *d_rt, uint32_t pitch,
                      uint32_t fmt) {
   const uint32_t tiles = fc.binsX * fc.binsY;
   int rc = ensure_bin_scratch(ctx, as->av.n, tiles, 0);
   if (rc) return rc;
   {  // raster-tile cost history (launch order); invalidated when the tile grid changes
-    const uint32_t rtiles = (((uint32_t)fc.screenW + kTile - 1) / kTile) * partition_own_bin_rows(opt, fc.binsY) * (kBin / kTile);
+    // per-tile state is indexed by the tile's id in the whole image, whatever part of it this context composites
+    const uint32_t rtiles = (((uint32_t)fc.screenW + kTile - 1) / kTile) * fc.binsY * (kBin / kTile);
     if (rtiles > ctx->raster_tiles_cap) {
       cudaStreamSynchronize(ctx->stream);
       cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order);
@@ -319,24 +270,50 @@ static int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const G
       ctx->raster_tiles_cur = rtiles;
     }
   }
-  int bin_passes = 0;
-  const BinScratch lists = launch_binning(fc, opt, as->av.n, as->order, as->rect, ctx->bin, ctx->sort, ctx->stream, &bin_passes);
+  int bin_launches = 0;
+  const BinScratch lists = launch_binning(fc, opt, as->av.n, as->order, as->rect, as->draw_mask, ctx->bin, ctx->sort, ctx->stream, &bin_launches);
   rec(ctx, EV_BIN1);
   launch_raster(fc, opt, as->draw, lists, d_rt, pitch, fmt, ctx->stream);
   rec(ctx, EV_RASTER1);
-  ctx->launches += 1 + bin_passes + 3;  // bin_emit, 1-2 sort passes, bin_ranges, tile_order, raster
+  ctx->launches += bin_launches + 3;  // compaction, bin_emit, look-back clear, 1-2 sort passes; bin_ranges, tile_order, raster
   GS_CUDA_TRY(ctx, cudaGetLastError());
   return GS_OK;
 }
 
 
-static int image_ok(GsContext *ctx, const GsImage *im, uint32_t W, uint32_t H, uint32_t *pitch) {
+int image_ok(GsContext *ctx, const GsImage *im, uint32_t W, uint32_t H, uint32_t *pitch) {
   if (!im || !im->data) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "image is null");
   if (im->format > GS_PIX_RGBA32F) return fail(ctx, GS_ERR_UNSUPPORTED_FORMAT, "unsupported pixel format");
   if (im->width != W || im->height != H) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "image size does not match screen size");
   uint32_t p = im->row_pitch_bytes ? im->row_pitch_bytes : W * pix_bytes(im->format);
   if (p < W * pix_bytes(im->format) || (p % pix_bytes(im->format)) != 0) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad row pitch");
   *pitch = p;
+  return GS_OK;
+}
+
+// options shared by gs_render / gs_frame: validated copy
+int check_options(GsContext *ctx, const FrameConsts &fc, GsRenderOptions &opt) {
+  if (opt.blend_mode > GS_BLEND_FP32) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad blend mode");
+  if (opt.row_end > opt.row_begin) {
+    const uint32_t rows = ((uint32_t)fc.screenH + kTile - 1) / kTile;
+    if (opt.row_end > rows) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "row_end beyond the last 16-pixel row of the screen");
+    opt.band_packed = 0; opt.partition_count = 0; opt.partition_index = 0;
+  } else {
+    opt.row_begin = opt.row_end = 0;
+  }
+  return GS_OK;
+}
+
+// what the compositor starts from in a device staging image: the host image's content (GS_FLAG_LOAD_RT), or zeros where a
+// partition leaves rows untouched
+static int init_staging(GsContext *ctx, const GsRenderOptions &opt, void *d_rt, uint32_t d_pitch, uint32_t W, uint32_t H, uint32_t fmt,
+                        const GsImage *host_rt, uint32_t host_pitch) {
+  if (opt.flags & GS_FLAG_LOAD_RT) {
+    if (host_rt) GS_CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rt, d_pitch, host_rt->data, host_pitch, (size_t)W * pix_bytes(fmt), H, cudaMemcpyHostToDevice, ctx->stream));
+    else GS_CUDA_TRY(ctx, cudaMemsetAsync(d_rt, 0, (size_t)d_pitch * H, ctx->stream));
+  } else if (opt.partition_count > 1 || opt.row_end > opt.row_begin) {
+    GS_CUDA_TRY(ctx, cudaMemsetAsync(d_rt, 0, (size_t)d_pitch * H, ctx->stream));
+  }
   return GS_OK;
 }
 
@@ -400,7 +377,7 @@ void gs_destroy(GsContext *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->sort.alt_keys); cudaFree(ctx->sort.alt_vals); cudaFree(ctx->sort.lookback);
   cudaFree(ctx->sort.ghist); cudaFree(ctx->sort.tickets); cudaFree(ctx->d_scalar);
-  cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
+  cudaFree(ctx->bin.list_ids); cudaFree(ctx->bin.cmp_status); cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
   cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (int i = 0; i < 2; ++i) {
@@ -497,7 +474,7 @@ int gs_asset_upload(GsContext *ctx, const GsAssetDesc *d, GsAsset **out) {
       (e = cudaMalloc(&as->order, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->keys, n * 4)) != cudaSuccess ||
       (e = cudaMalloc(&as->key_table, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->draw, n * 48)) != cudaSuccess ||
       (e = cudaMalloc(&as->view, n * kViewStride + 16)) != cudaSuccess || (e = cudaMalloc(&as->rect, n * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&as->d_n, 4)) != cudaSuccess) {
+      (e = cudaMalloc(&as->d_n, 4)) != cudaSuccess || (e = cudaMalloc(&as->draw_mask, ((n + 255) / 256) * 32 + 64)) != cudaSuccess) {
     gs_asset_destroy(as);
     return fail_cuda(ctx, e, "asset upload", __FILE__, __LINE__);
   }
@@ -519,7 +496,7 @@ void gs_asset_destroy(GsAsset *as) {
   if (!as) return;
   if (as->ctx) { cudaSetDevice(as->ctx->device); cudaStreamSynchronize(as->ctx->stream); }
   cudaFree(as->d_pos); cudaFree(as->d_other); cudaFree(as->d_sh); cudaFree(as->d_color); cudaFree(as->d_chunks);
-  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->draw); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n);
+  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->draw); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n); cudaFree(as->draw_mask); cudaFree(as->slab_mask); cudaFree(as->order_tmp);
   delete as;
 }
 
@@ -546,7 +523,7 @@ int gs_calc_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
   if (rc) return rc;
   for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
   FrameConsts fc = make_frame_consts(fp);
-  return do_view(ctx, as, fp, fc, false, default_opts());
+  return do_view(ctx, as, fp, fc, false, default_opts(), ctx->stream);
 }
 
 int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRenderOptions *opt_in, GsImage *rt) {
@@ -557,13 +534,14 @@ int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRend
   const uint32_t W = (uint32_t)fp->screen_w;
   uint32_t pitch = 0;
   GsRenderOptions opt = opt_in ? *opt_in : default_opts();
-  if (opt.blend_mode > GS_BLEND_FP32) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad blend mode");
+  FrameConsts fc = make_frame_consts(fp);
+  if ((rc = check_options(ctx, fc, opt))) return rc;
   {
     const gs::Partition p = make_partition(opt);
-    if (as->draw_part[1] > 1 && (as->draw_part[0] != p.index || as->draw_part[1] != p.count || as->draw_part[2] != p.band))
+    const uint32_t want[3] = {p.range ? p.t0 : p.index, p.range ? 0xFFFFFFFFu : p.count, p.range ? p.t1 : p.band};
+    if (as->draw_part[1] > 1 && (as->draw_part[0] != want[0] || as->draw_part[1] != want[1] || as->draw_part[2] != want[2]))
       return fail(ctx, GS_ERR_NOT_READY, "the last gs_frame prepared draw records for another tile partition; run gs_calc_view");
   }
-  FrameConsts fc = make_frame_consts(fp);
   const uint32_t H = opt.band_packed ? partition_own_bin_rows(opt, fc.binsY) * kBin : (uint32_t)fp->screen_h;
   if ((rc = image_ok(ctx, rt, W, H, &pitch))) return rc;
   for (int e = EV_BIN1; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
@@ -571,7 +549,7 @@ int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRend
   if (rt->memory == GS_MEM_DEVICE) return do_render(ctx, as, fc, opt, rt->data, pitch, rt->format);
   const uint32_t tight = W * pix_bytes(rt->format);
   if ((rc = grow(ctx, &ctx->rt_scratch, &ctx->rt_bytes, (size_t)tight * H))) return rc;
-  if (opt.partition_count > 1) GS_CUDA_TRY(ctx, cudaMemsetAsync(ctx->rt_scratch, 0, (size_t)tight * H, ctx->stream));
+  if ((rc = init_staging(ctx, opt, ctx->rt_scratch, tight, W, H, rt->format, rt, pitch))) return rc;
   if ((rc = do_render(ctx, as, fc, opt, ctx->rt_scratch, tight, rt->format))) return rc;
   GS_CUDA_TRY(ctx, cudaMemcpy2DAsync(rt->data, pitch, ctx->rt_scratch, tight, tight, H, cudaMemcpyDeviceToHost, ctx->stream));
   return check_bin_overflow(ctx);
@@ -619,15 +597,15 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
   if (!rt && !tgt) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "gs_frame needs rt and/or camera_target");
   const uint32_t W = (uint32_t)fp->screen_w;
   GsRenderOptions opt = opt_in ? *opt_in : default_opts();
-  if (opt.blend_mode > GS_BLEND_FP32) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad blend mode");
   uint32_t rt_pitch = 0, rt_fmt = GS_PIX_RGBA16F;
   FrameConsts fc = make_frame_consts(fp);
+  if ((rc = check_options(ctx, fc, opt))) return rc;
   const uint32_t H = opt.band_packed ? partition_own_bin_rows(opt, fc.binsY) * kBin : (uint32_t)fp->screen_h;
   if (opt.band_packed && tgt) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "band_packed output cannot be composited before the gather");
   if (rt) { if ((rc = image_ok(ctx, rt, W, H, &rt_pitch))) return rc; rt_fmt = rt->format; }
   for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
   if (do_sort_flag && (rc = do_sort(ctx, as, fc))) return rc;
-  if ((rc = do_view(ctx, as, fp, fc, true, opt))) return rc;   // fused frame: colour of never-drawn splats is dead code
+  if ((rc = do_view(ctx, as, fp, fc, true, opt, ctx->stream))) return rc;   // fused frame: colour of never-drawn splats is dead code
   void *d_rt;
   uint32_t d_pitch;
   const bool rt_dev = rt && rt->memory == GS_MEM_DEVICE;
@@ -644,12 +622,12 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
     if (ctx->rt_async_bytes[slot] < (size_t)d_pitch * H && ctx->copy_pending[slot]) GS_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));  // about to be freed
     if ((rc = grow(ctx, &ctx->rt_async[slot], &ctx->rt_async_bytes[slot], (size_t)d_pitch * H))) return rc;
     d_rt = ctx->rt_async[slot];
-    if (opt.partition_count > 1) GS_CUDA_TRY(ctx, cudaMemsetAsync(d_rt, 0, (size_t)d_pitch * H, ctx->stream));
+    if ((rc = init_staging(ctx, opt, d_rt, d_pitch, W, H, rt_fmt, rt, rt_pitch))) return rc;
   } else {
     d_pitch = W * pix_bytes(rt_fmt);
     if ((rc = grow(ctx, &ctx->rt_scratch, &ctx->rt_bytes, (size_t)d_pitch * H))) return rc;
     d_rt = ctx->rt_scratch;
-    if (opt.partition_count > 1) GS_CUDA_TRY(ctx, cudaMemsetAsync(d_rt, 0, (size_t)d_pitch * H, ctx->stream));
+    if ((rc = init_staging(ctx, opt, d_rt, d_pitch, W, H, rt_fmt, rt, rt_pitch))) return rc;
   }
   if ((rc = do_render(ctx, as, fc, opt, d_rt, d_pitch, rt_fmt))) return rc;
   bool synced = false;
@@ -755,7 +733,7 @@ int gs_export_splats(GsContext *ctx, GsAsset *as, const GsCutout *cutouts, uint3
   GsFrameParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.cutouts = cutouts; fp.cutout_count = cutout_count;
-  int rc = upload_frame_inputs(ctx, as, &fp);
+  int rc = upload_frame_inputs(ctx, as, &fp, ctx->stream);
   if (rc != GS_OK) return rc;
   float *d_out = nullptr;
   const size_t bytes = (size_t)as->av.n * 62 * sizeof(float);

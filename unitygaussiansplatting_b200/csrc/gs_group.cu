@@ -1,0 +1,577 @@
+// gs_group.cu -- one frame on the G GPUs of one box (include/gsplat_b200.h, "several GPUs"; SURVEY 8e.1 + 8e.2).
+//
+// The reference is single-GPU; what a group must reproduce is its per-frame contract: after SortPoints the persistent order
+// buffer holds the stable ascending sort of the depth keys taken through last frame's order (R/GaussianSplatRenderer.cs:612-639,
+// R/GpuSorting.cs:142-198), and the render target holds the front-to-back blend of every splat in that order
+// (S/RenderGaussianSplats.shader:10-12,79-108).  Both come out bit-identical to gs_frame on one GPU, because
+//   * the sort is sharded by KEY RANGE.  Splitters are the current keys of the splats at the quantile positions of last
+//     frame's order (replicated data -> the same values on every GPU).  GPU g compacts, out of last frame's order, the
+//     splats of slab g -- keys in [splitter g-1, splitter g) -- and radix-sorts only those.  A stable sort of a
+//     subsequence is the subsequence of the stable sort, ties never straddle a splitter, so the slabs concatenated ARE
+//     the single-GPU order.  Slab sizes fall out of the distance kernel on every GPU (counts of keys >= each splitter),
+//     so every GPU knows every offset and the exchange needs no size negotiation;
+//   * every pixel is composited by exactly one GPU, from the same per-bin list in the same order.  Each GPU owns a
+//     contiguous range of 16-pixel rows, culls view-calc / binning to it, composites straight into place; the ranges are
+//     re-cut every frame from the per-row cost measured two frames earlier (exchanged with the pixels), which is the
+//     same on every GPU, so the cuts agree without a negotiation either.
+// Streams: the sort chain and the compositing chain run on the context stream, view-calc beside the sort on a second
+// stream; the only host wait inside a frame is for the 128-byte slab table (the GPU is busy with view-calc meanwhile).
+// Exchanges are grouped NCCL broadcasts in place (an all-gather with per-rank sizes); in GS_GROUP_EMULATE, or without NCCL in
+// a single process, plain device-to-device copies ordered by events.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "gs_internal.cuh"
+#include "gs_nccl.h"
+
+using namespace gs;
+
+namespace {
+
+enum { GT_BEGIN = 0, GT_DIST, GT_SORT, GT_ORDER, GT_VIEWWAIT, GT_RASTER, GT_IMAGE, GT_V0, GT_V1, GT_COUNT };
+
+struct Member {
+  GsContext *ctx = nullptr;
+  bool own_ctx = false;
+  uint32_t rank = 0;
+  ncclComm_t comm = nullptr;
+  cudaStream_t aux = nullptr;   // view-calc runs here, beside the sort chain
+  cudaEvent_t ev_begin = nullptr, ev_view = nullptr, ev_info = nullptr, ev_cost[2] = {nullptr, nullptr};
+  cudaEvent_t ev_produced = nullptr, ev_consumed = nullptr;   // emulated exchange
+  cudaEvent_t tev[GT_COUNT]{};
+  uint32_t *d_info = nullptr, *d_slab_count = nullptr, *d_cmp_status = nullptr, *d_row_cost = nullptr;
+  size_t cmp_words = 0;
+  uint32_t rows_cap = 0;
+  uint32_t *h_info = nullptr, *h_row_cost[2] = {nullptr, nullptr};   // pinned
+  void *rt_scratch = nullptr;
+  size_t rt_bytes = 0;
+};
+
+}  // namespace
+
+struct GsGroup {
+  uint32_t size = 0;
+  std::vector<Member> m;
+  bool emulate = false, use_nccl = false;
+  int xfer = 0;   // 0: grouped broadcasts, 1: grouped send/recv  (GS_GROUP_XFER=bcast|sendrecv)
+  uint64_t frame = 0;
+  uint32_t hist_w = 0, hist_h = 0;
+  uint64_t hist_frames = 0;   // frames rendered at (hist_w, hist_h): the cost of frame k is usable from frame k+2 on
+  uint32_t bounds[GS_GROUP_MAX_GPUS + 1]{};
+  uint32_t slab_off[GS_GROUP_MAX_GPUS + 1]{}, slab_cnt[GS_GROUP_MAX_GPUS]{};
+  bool timed = false;
+};
+
+namespace {
+
+int fail_nccl(GsContext *ctx, ncclResult_t r, const char *what) {
+  char buf[256];
+  snprintf(buf, sizeof(buf), "NCCL error %d (%s) in %s", (int)r, nccl_api().GetErrorString ? nccl_api().GetErrorString(r) : "?", what);
+  return fail(ctx, GS_ERR_CUDA, buf);
+}
+#define GS_NCCL_TRY(ctx, expr)                                   \
+  do {                                                           \
+    ncclResult_t _r = (expr);                                    \
+    if (_r != ncclSuccess) return fail_nccl((ctx), _r, #expr);   \
+  } while (0)
+
+int member_init(Member &mb) {
+  GsContext *ctx = mb.ctx;
+  GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  GS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&mb.aux, cudaStreamNonBlocking));
+  cudaEvent_t *evs[] = {&mb.ev_begin, &mb.ev_view, &mb.ev_info, &mb.ev_cost[0], &mb.ev_cost[1], &mb.ev_produced, &mb.ev_consumed};
+  for (cudaEvent_t *e : evs) GS_CUDA_TRY(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  for (int i = 0; i < GT_COUNT; ++i) GS_CUDA_TRY(ctx, cudaEventCreate(&mb.tev[i]));
+  GS_CUDA_TRY(ctx, cudaMalloc(&mb.d_info, 2 * kMaxSlabs * 4));
+  GS_CUDA_TRY(ctx, cudaMalloc(&mb.d_slab_count, 16));
+  GS_CUDA_TRY(ctx, cudaMallocHost(&mb.h_info, 2 * kMaxSlabs * 4));
+  return GS_OK;
+}
+
+void member_free(Member &mb) {
+  if (!mb.ctx) return;
+  cudaSetDevice(mb.ctx->device);
+  cudaStreamSynchronize(mb.ctx->stream);
+  if (mb.aux) { cudaStreamSynchronize(mb.aux); cudaStreamDestroy(mb.aux); }
+  cudaEvent_t evs[] = {mb.ev_begin, mb.ev_view, mb.ev_info, mb.ev_cost[0], mb.ev_cost[1], mb.ev_produced, mb.ev_consumed};
+  for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < GT_COUNT; ++i) if (mb.tev[i]) cudaEventDestroy(mb.tev[i]);
+  cudaFree(mb.d_info); cudaFree(mb.d_slab_count); cudaFree(mb.d_cmp_status); cudaFree(mb.d_row_cost); cudaFree(mb.rt_scratch);
+  cudaFreeHost(mb.h_info); cudaFreeHost(mb.h_row_cost[0]); cudaFreeHost(mb.h_row_cost[1]);
+  if (mb.comm && nccl_api().ok()) nccl_api().CommDestroy(mb.comm);
+  if (mb.own_ctx) gs_destroy(mb.ctx);
+  mb.ctx = nullptr;
+}
+
+int member_rows(Member &mb, uint32_t rows) {   // row-cost vectors for a screen of `rows` 16-pixel rows
+  if (rows <= mb.rows_cap) return GS_OK;
+  GsContext *ctx = mb.ctx;
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(mb.d_row_cost); cudaFreeHost(mb.h_row_cost[0]); cudaFreeHost(mb.h_row_cost[1]);
+  mb.d_row_cost = nullptr; mb.h_row_cost[0] = mb.h_row_cost[1] = nullptr; mb.rows_cap = 0;
+  GS_CUDA_TRY(ctx, cudaMalloc(&mb.d_row_cost, (size_t)rows * 4));
+  GS_CUDA_TRY(ctx, cudaMallocHost(&mb.h_row_cost[0], (size_t)rows * 4));
+  GS_CUDA_TRY(ctx, cudaMallocHost(&mb.h_row_cost[1], (size_t)rows * 4));
+  mb.rows_cap = rows;
+  return GS_OK;
+}
+
+int member_asset(Member &mb, GsAsset *as) {   // per-asset buffers only the group path needs
+  GsContext *ctx = mb.ctx;
+  const uint32_t n = as->av.n;
+  if (!as->slab_mask) GS_CUDA_TRY(ctx, cudaMalloc(&as->slab_mask, ((size_t)(n + 1023) / 1024) * 128 + 64));
+  if (!as->order_tmp) GS_CUDA_TRY(ctx, cudaMalloc(&as->order_tmp, (size_t)n * 4 + 16));
+  const size_t words = compact_status_words(n);
+  if (words > mb.cmp_words) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(mb.d_cmp_status);
+    mb.d_cmp_status = nullptr; mb.cmp_words = 0;
+    GS_CUDA_TRY(ctx, cudaMalloc(&mb.d_cmp_status, words * 4));
+    mb.cmp_words = words;
+  }
+  return ensure_sort_scratch(ctx, n);
+}
+
+// ---- the exchange: every member ends up with every segment ------------------------------------------------------------
+// bufs[i]: local member i's copy of the whole buffer; segment c = bytes [off[c], off[c] + cnt[c]) is produced by rank c.
+int exchange_begin(GsGroup *g) {
+  if (g->use_nccl) GS_NCCL_TRY(g->m[0].ctx, nccl_api().GroupStart());
+  return GS_OK;
+}
+int exchange_add(GsGroup *g, uint8_t *const *bufs, const size_t *off, const size_t *cnt) {
+  const uint32_t G = g->size;
+  if (g->use_nccl) {
+    const NcclApi &nc = nccl_api();
+    for (size_t i = 0; i < g->m.size(); ++i) {
+      Member &mb = g->m[i];
+      if (g->xfer == 1) {
+        for (uint32_t p = 0; p < G; ++p) {
+          if (p == mb.rank) continue;
+          if (cnt[mb.rank]) GS_NCCL_TRY(mb.ctx, nc.Send(bufs[i] + off[mb.rank], cnt[mb.rank], ncclUint8, (int)p, mb.comm, mb.ctx->stream));
+          if (cnt[p]) GS_NCCL_TRY(mb.ctx, nc.Recv(bufs[i] + off[p], cnt[p], ncclUint8, (int)p, mb.comm, mb.ctx->stream));
+        }
+      } else {
+        for (uint32_t c = 0; c < G; ++c)
+          if (cnt[c]) GS_NCCL_TRY(mb.ctx, nc.Broadcast(bufs[i] + off[c], bufs[i] + off[c], cnt[c], ncclUint8, (int)c, mb.comm, mb.ctx->stream));
+      }
+    }
+    return GS_OK;
+  }
+  // all ranks are local members (member i == rank i): copies ordered by events, with barrier semantics like a collective
+  for (Member &mb : g->m) { cudaSetDevice(mb.ctx->device); GS_CUDA_TRY(mb.ctx, cudaEventRecord(mb.ev_produced, mb.ctx->stream)); }
+  for (uint32_t d = 0; d < G; ++d) {
+    Member &dst = g->m[d];
+    cudaSetDevice(dst.ctx->device);
+    for (uint32_t c = 0; c < G; ++c) {
+      if (c == d || !cnt[c]) continue;
+      GS_CUDA_TRY(dst.ctx, cudaStreamWaitEvent(dst.ctx->stream, g->m[c].ev_produced, 0));
+      GS_CUDA_TRY(dst.ctx, cudaMemcpyAsync(bufs[d] + off[c], bufs[c] + off[c], cnt[c], cudaMemcpyDefault, dst.ctx->stream));
+    }
+    GS_CUDA_TRY(dst.ctx, cudaEventRecord(dst.ev_consumed, dst.ctx->stream));
+  }
+  for (uint32_t c = 0; c < G; ++c) {
+    cudaSetDevice(g->m[c].ctx->device);
+    for (uint32_t d = 0; d < G; ++d)
+      if (d != c) GS_CUDA_TRY(g->m[c].ctx, cudaStreamWaitEvent(g->m[c].ctx->stream, g->m[d].ev_consumed, 0));
+  }
+  return GS_OK;
+}
+int exchange_end(GsGroup *g) {
+  if (g->use_nccl) GS_NCCL_TRY(g->m[0].ctx, nccl_api().GroupEnd());
+  return GS_OK;
+}
+
+void balance_rows(const uint32_t *cost, uint32_t rows, uint32_t parts, uint32_t *bounds) {
+  // every row also carries a fixed share (its tiles are launched, its pixels stored) so that empty rows are not free
+  uint64_t sum = 0;
+  for (uint32_t r = 0; r < rows; ++r) sum += cost ? cost[r] : 0u;
+  const uint64_t base = sum / ((uint64_t)rows * 8u) + 1u;
+  const uint64_t total = sum + base * rows;
+  uint64_t acc = 0;
+  uint32_t r = 0;
+  bounds[0] = 0;
+  for (uint32_t p = 1; p < parts; ++p) {
+    const uint64_t target = total * p / parts;
+    while (r < rows) {
+      const uint64_t w = (cost ? cost[r] : 0u) + base;
+      if (acc + w / 2 >= target) break;   // a row goes to the part its midpoint falls into
+      acc += w;
+      ++r;
+    }
+    bounds[p] = r;
+  }
+  bounds[parts] = rows;
+}
+
+float tev_ms(Member &mb, int a, int b) {
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, mb.tev[a], mb.tev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0f; }
+  return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gs_group_balance_rows(const uint32_t *row_cost, uint32_t rows, uint32_t parts, uint32_t *bounds_out) {
+  if (!bounds_out || rows == 0 || parts == 0 || parts > GS_GROUP_MAX_GPUS) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "bad rows/parts");
+  balance_rows(row_cost, rows, parts, bounds_out);
+  return GS_OK;
+}
+
+int gs_group_unique_id(void *id_out) {
+  if (!id_out) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "null id");
+  if (!nccl_api().ok()) return fail(nullptr, GS_ERR_NOT_READY, "libnccl.so.2 not found: a multi-process group needs NCCL");
+  ncclUniqueId id;
+  GS_NCCL_TRY(nullptr, nccl_api().GetUniqueId(&id));
+  static_assert(sizeof(id) == GS_GROUP_ID_BYTES, "id size");
+  memcpy(id_out, &id, sizeof(id));
+  return GS_OK;
+}
+
+static int group_env(GsGroup *g) {
+  const char *x = getenv("GS_GROUP_XFER");
+  g->xfer = (x && !strcmp(x, "sendrecv")) ? 1 : 0;
+  return GS_OK;
+}
+
+int gs_group_join(GsContext *ctx, uint32_t group_size, uint32_t rank, const void *id, GsGroup **out) {
+  if (!ctx || !out || !id || group_size == 0 || group_size > GS_GROUP_MAX_GPUS || rank >= group_size)
+    return fail(ctx, GS_ERR_INVALID_ARGUMENT, "bad group size / rank / id");
+  *out = nullptr;
+  if (!nccl_api().ok()) return fail(ctx, GS_ERR_NOT_READY, "libnccl.so.2 not found: a multi-process group needs NCCL");
+  GsGroup *g = new (std::nothrow) GsGroup();
+  if (!g) return fail(ctx, GS_ERR_OUT_OF_MEMORY, "host allocation failed");
+  g->size = group_size;
+  g->use_nccl = true;
+  group_env(g);
+  g->m.resize(1);
+  g->m[0].ctx = ctx;
+  g->m[0].rank = rank;
+  int rc = member_init(g->m[0]);
+  if (rc == GS_OK) {
+    ncclUniqueId nid;
+    memcpy(&nid, id, sizeof(nid));
+    ncclResult_t r = nccl_api().CommInitRank(&g->m[0].comm, (int)group_size, nid, (int)rank);
+    if (r != ncclSuccess) rc = fail_nccl(ctx, r, "ncclCommInitRank");
+  }
+  if (rc != GS_OK) { gs_group_destroy(g); return rc; }
+  *out = g;
+  return GS_OK;
+}
+
+int gs_group_create(const int *devices, uint32_t n, uint32_t flags, GsGroup **out) {
+  if (!devices || !out || n == 0 || n > GS_GROUP_MAX_GPUS) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "bad device list");
+  *out = nullptr;
+  bool distinct = true;
+  for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t j = 0; j < i; ++j) distinct &= devices[i] != devices[j];
+  if (!distinct && !(flags & GS_GROUP_EMULATE)) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "a device is listed twice (only GS_GROUP_EMULATE allows that)");
+  GsGroup *g = new (std::nothrow) GsGroup();
+  if (!g) return fail(nullptr, GS_ERR_OUT_OF_MEMORY, "host allocation failed");
+  g->size = n;
+  g->emulate = (flags & GS_GROUP_EMULATE) != 0;
+  group_env(g);
+  g->m.resize(n);
+  int rc = GS_OK;
+  for (uint32_t i = 0; i < n && rc == GS_OK; ++i) {
+    GsContext *ctx = nullptr;
+    rc = gs_create(devices[i], nullptr, &ctx);
+    if (rc != GS_OK) break;
+    g->m[i].ctx = ctx;
+    g->m[i].own_ctx = true;
+    g->m[i].rank = i;
+    rc = member_init(g->m[i]);
+  }
+  if (rc == GS_OK && !g->emulate && n > 1) {
+    const char *force = getenv("GS_GROUP_NO_NCCL");
+    if (nccl_api().ok() && !(force && force[0] == '1')) {
+      std::vector<ncclComm_t> comms(n);
+      ncclResult_t r = nccl_api().CommInitAll(comms.data(), (int)n, devices);
+      if (r != ncclSuccess) rc = fail_nccl(nullptr, r, "ncclCommInitAll");
+      else { for (uint32_t i = 0; i < n; ++i) g->m[i].comm = comms[i]; g->use_nccl = true; }
+    } else {   // device-to-device copies between the contexts: let them go straight over NVLink
+      for (uint32_t i = 0; i < n; ++i) {
+        cudaSetDevice(devices[i]);
+        for (uint32_t j = 0; j < n; ++j) {
+          int can = 0;
+          if (i != j && cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) == cudaSuccess && can) cudaDeviceEnablePeerAccess(devices[j], 0);
+        }
+        cudaGetLastError();
+      }
+    }
+  }
+  if (rc != GS_OK) { gs_group_destroy(g); return rc; }
+  *out = g;
+  return GS_OK;
+}
+
+void gs_group_destroy(GsGroup *g) {
+  if (!g) return;
+  for (Member &mb : g->m) member_free(mb);
+  delete g;
+}
+
+uint32_t gs_group_size(const GsGroup *g) { return g ? g->size : 0; }
+uint32_t gs_group_local_count(const GsGroup *g) { return g ? (uint32_t)g->m.size() : 0; }
+GsContext *gs_group_context(GsGroup *g, uint32_t i) { return (g && i < g->m.size()) ? g->m[i].ctx : nullptr; }
+
+int gs_group_asset_upload(GsGroup *g, const GsAssetDesc *desc, GsAsset **assets_out) {
+  if (!g || !desc || !assets_out) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "null argument");
+  for (size_t i = 0; i < g->m.size(); ++i) assets_out[i] = nullptr;
+  for (size_t i = 0; i < g->m.size(); ++i) {
+    int rc = gs_asset_upload(g->m[i].ctx, desc, &assets_out[i]);
+    if (rc == GS_OK) { cudaSetDevice(g->m[i].ctx->device); rc = member_asset(g->m[i], assets_out[i]); }
+    if (rc != GS_OK) {
+      for (size_t j = 0; j <= i; ++j) { gs_asset_destroy(assets_out[j]); assets_out[j] = nullptr; }
+      return rc;
+    }
+  }
+  return GS_OK;
+}
+
+int gs_group_sync(GsGroup *g) {
+  if (!g) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "null group");
+  int rc = GS_OK;
+  for (Member &mb : g->m) {
+    cudaSetDevice(mb.ctx->device);
+    cudaError_t e = cudaStreamSynchronize(mb.aux);
+    if (e != cudaSuccess && rc == GS_OK) rc = fail_cuda(mb.ctx, e, "cudaStreamSynchronize(aux)", __FILE__, __LINE__);
+    const int r = gs_sync(mb.ctx);
+    if (r != GS_OK && rc == GS_OK) rc = r;
+  }
+  return rc;
+}
+
+int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, const GsRenderOptions *opt_in, int do_sort_flag,
+                   GsImage *const *rts) {
+  if (!g || !assets || !fp) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "null argument");
+  const uint32_t G = g->size;
+  const size_t L = g->m.size();
+  int rc;
+  for (size_t i = 0; i < L; ++i) {
+    if (!assets[i]) return fail(g->m[i].ctx, GS_ERR_INVALID_ARGUMENT, "null asset");
+    if ((rc = check_params(g->m[i].ctx, assets[i], fp))) return rc;
+    if (assets[i]->av.n != assets[0]->av.n) return fail(g->m[i].ctx, GS_ERR_INVALID_ARGUMENT, "members hold different assets");
+  }
+  const FrameConsts fc = make_frame_consts(fp);
+  const uint32_t W = (uint32_t)fp->screen_w, H = (uint32_t)fp->screen_h, N = assets[0]->av.n;
+  const uint32_t rows = (H + kTile - 1) / kTile, ntx = (W + kTile - 1) / kTile;
+  GsRenderOptions base;
+  memset(&base, 0, sizeof(base));
+  base.blend_mode = opt_in ? opt_in->blend_mode : (uint32_t)GS_BLEND_FP16_ROP;
+  if (base.blend_mode > GS_BLEND_FP32) return fail(g->m[0].ctx, GS_ERR_INVALID_ARGUMENT, "bad blend mode");
+  uint32_t fmt = GS_PIX_RGBA16F;
+  for (size_t i = 0; i < L; ++i) if (rts && rts[i]) { fmt = rts[i]->format; break; }
+
+  // ---- row ranges of this frame: from the row costs measured two frames ago (the last ones every GPU surely holds) ----
+  if (g->hist_w != W || g->hist_h != H) { g->hist_w = W; g->hist_h = H; g->hist_frames = 0; }
+  const int slot = (int)(g->hist_frames & 1u);
+  for (Member &mb : g->m) { cudaSetDevice(mb.ctx->device); if ((rc = member_rows(mb, rows))) return rc; }
+  if (G == 1) { g->bounds[0] = 0; g->bounds[1] = rows; }
+  else if (g->hist_frames >= 2) {
+    Member &m0 = g->m[0];
+    GS_CUDA_TRY(m0.ctx, cudaEventSynchronize(m0.ev_cost[slot]));   // written by frame hist_frames - 2: long done
+    balance_rows(m0.h_row_cost[slot], rows, G, g->bounds);
+  } else {
+    balance_rows(nullptr, rows, G, g->bounds);
+  }
+
+  const bool timing = g->m[0].ctx->timing;
+  g->timed = timing;
+  // ---- phase A: distances + slab table on the context stream; view-calc on the second stream --------------------------
+  for (size_t i = 0; i < L; ++i) {
+    Member &mb = g->m[i];
+    GsContext *ctx = mb.ctx;
+    GsAsset *as = assets[i];
+    GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if ((rc = member_asset(mb, as))) return rc;
+    for (int e = 0; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
+    GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_begin, ctx->stream));
+    if (timing) cudaEventRecord(mb.tev[GT_BEGIN], ctx->stream);
+    if (do_sort_flag) {
+      SlabArgs sl;
+      memset(&sl, 0, sizeof(sl));
+      sl.count = G; sl.index = mb.rank; sl.order_prev = as->order; sl.mask = as->slab_mask; sl.info = mb.d_info;
+      for (uint32_t j = 0; j + 1 < G; ++j) sl.qpos[j] = (uint32_t)(((uint64_t)N * (j + 1)) / G);
+      GS_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sort.ghist, 0, 4 * 256 * 4, ctx->stream));
+      GS_CUDA_TRY(ctx, cudaMemsetAsync(mb.d_info, 0, 2 * kMaxSlabs * 4, ctx->stream));
+      launch_calc_distances(as->av, fc, as->key_table, ctx->sort.ghist, ctx->stream, &sl);
+      ctx->launches += 1;
+      if (G > 1) {
+        GS_CUDA_TRY(ctx, cudaMemcpyAsync(mb.h_info, mb.d_info, 2 * kMaxSlabs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_info, ctx->stream));
+      }
+    }
+    if (timing) cudaEventRecord(mb.tev[GT_DIST], ctx->stream);
+    // view-calc reads nothing the sort writes; it must only wait for whatever used rect / draw records before this frame
+    GsRenderOptions opt = base;
+    opt.row_begin = g->bounds[mb.rank]; opt.row_end = g->bounds[mb.rank + 1];
+    if (opt.row_end > opt.row_begin || G == 1) {
+      if (G == 1) opt.row_begin = opt.row_end = 0;
+      GS_CUDA_TRY(ctx, cudaStreamWaitEvent(mb.aux, mb.ev_begin, 0));
+      if (timing) cudaEventRecord(mb.tev[GT_V0], mb.aux);
+      if ((rc = do_view(ctx, as, fp, fc, true, opt, mb.aux))) return rc;
+      if (timing) cudaEventRecord(mb.tev[GT_V1], mb.aux);
+      GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_view, mb.aux));
+    }
+  }
+
+  // ---- slab sizes: the one host wait of the frame (the GPUs are busy with view-calc) ----------------------------------
+  if (do_sort_flag) {
+    if (G == 1) { g->slab_off[0] = 0; g->slab_off[1] = N; g->slab_cnt[0] = N; }
+    for (size_t i = 0; i < L && G > 1; ++i) {
+      Member &mb = g->m[i];
+      GS_CUDA_TRY(mb.ctx, cudaSetDevice(mb.ctx->device));
+      GS_CUDA_TRY(mb.ctx, cudaEventSynchronize(mb.ev_info));
+      uint32_t off[GS_GROUP_MAX_GPUS + 1];
+      off[0] = 0;
+      for (uint32_t c = 1; c < G; ++c) {
+        const uint32_t ge = mb.h_info[kMaxSlabs + c - 1];   // #{key >= splitter c-1 (ascending)}
+        if (ge > N) return fail(mb.ctx, GS_ERR_CUDA, "slab table corrupt");
+        off[c] = N - ge;
+      }
+      off[G] = N;
+      for (uint32_t c = 0; c < G; ++c) if (off[c + 1] < off[c]) return fail(mb.ctx, GS_ERR_CUDA, "slab table not monotone");
+      if (i == 0) memcpy(g->slab_off, off, sizeof(uint32_t) * (G + 1));
+      else if (memcmp(g->slab_off, off, sizeof(uint32_t) * (G + 1)) != 0) return fail(mb.ctx, GS_ERR_CUDA, "members disagree on the slab table");
+    }
+    for (uint32_t c = 0; c < G; ++c) g->slab_cnt[c] = g->slab_off[c + 1] - g->slab_off[c];
+
+    // ---- phase C: compact my slab out of last frame's order, sort it into its place of the new order ------------------
+    for (size_t i = 0; i < L; ++i) {
+      Member &mb = g->m[i];
+      GsContext *ctx = mb.ctx;
+      GsAsset *as = assets[i];
+      GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+      const uint32_t cnt = g->slab_cnt[mb.rank], off = g->slab_off[mb.rank];
+      if (G == 1) {
+        launch_sort_pairs(as->keys, as->order, as->d_n, N, 4, 8, true, ctx->sort, ctx->stream, nullptr, as->key_table);
+        ctx->launches += 4;
+      } else if (cnt) {
+        launch_compact_order(as->order, N, as->slab_mask, as->key_table, as->order_tmp, as->keys, mb.d_cmp_status, mb.d_slab_count, ctx->stream);
+        launch_sort_pairs(as->keys, as->order_tmp, mb.d_slab_count, cnt, 4, 8, true, ctx->sort, ctx->stream, nullptr, nullptr, true,
+                          as->keys + off, as->order + off);
+        ctx->launches += 5;
+      }
+      GS_CUDA_TRY(ctx, cudaGetLastError());
+      if (timing) cudaEventRecord(mb.tev[GT_SORT], ctx->stream);
+    }
+    if (G > 1) {
+      std::vector<uint8_t *> bufs(L);
+      size_t off[GS_GROUP_MAX_GPUS], cnt[GS_GROUP_MAX_GPUS];
+      for (uint32_t c = 0; c < G; ++c) { off[c] = (size_t)g->slab_off[c] * 4; cnt[c] = (size_t)g->slab_cnt[c] * 4; }
+      for (size_t i = 0; i < L; ++i) bufs[i] = reinterpret_cast<uint8_t *>(assets[i]->order);
+      if ((rc = exchange_begin(g)) || (rc = exchange_add(g, bufs.data(), off, cnt)) || (rc = exchange_end(g))) return rc;
+    }
+  }
+  if (timing) for (Member &mb : g->m) { cudaSetDevice(mb.ctx->device); if (!do_sort_flag) cudaEventRecord(mb.tev[GT_SORT], mb.ctx->stream); cudaEventRecord(mb.tev[GT_ORDER], mb.ctx->stream); }
+
+  // ---- phase D: bin + composite my rows, then exchange rows and row costs ---------------------------------------------
+  std::vector<uint8_t *> img(L), costs(L);
+  std::vector<uint32_t> pitches(L);
+  for (size_t i = 0; i < L; ++i) {
+    Member &mb = g->m[i];
+    GsContext *ctx = mb.ctx;
+    GsAsset *as = assets[i];
+    GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    GsImage *rt = rts ? rts[i] : nullptr;
+    uint32_t pitch = W * pix_bytes(fmt);
+    void *d_rt = nullptr;
+    if (rt) {
+      uint32_t p = 0;
+      if ((rc = image_ok(ctx, rt, W, H, &p))) return rc;
+      if (rt->format != fmt) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "members' images differ in pixel format");
+      if (rt->memory == GS_MEM_DEVICE) { d_rt = rt->data; pitch = p; }
+    }
+    if (!d_rt) {
+      if (mb.rt_bytes < (size_t)pitch * H) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(mb.rt_scratch);
+        mb.rt_scratch = nullptr; mb.rt_bytes = 0;
+        GS_CUDA_TRY(ctx, cudaMalloc(&mb.rt_scratch, (size_t)pitch * H));
+        mb.rt_bytes = (size_t)pitch * H;
+      }
+      d_rt = mb.rt_scratch;
+    }
+    img[i] = reinterpret_cast<uint8_t *>(d_rt);
+    pitches[i] = pitch;
+    costs[i] = reinterpret_cast<uint8_t *>(mb.d_row_cost);
+    GsRenderOptions opt = base;
+    opt.row_begin = g->bounds[mb.rank]; opt.row_end = g->bounds[mb.rank + 1];
+    if (opt.row_end > opt.row_begin || G == 1) {
+      if (G == 1) opt.row_begin = opt.row_end = 0;
+      GS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, mb.ev_view, 0));
+      if (timing) cudaEventRecord(mb.tev[GT_VIEWWAIT], ctx->stream);
+      rec(ctx, EV_VIEW1);
+      if ((rc = do_render(ctx, as, fc, opt, d_rt, pitch, fmt))) return rc;
+      launch_row_costs(ctx->bin.tile_cost, ntx, g->bounds[mb.rank], g->bounds[mb.rank + 1], mb.d_row_cost, ctx->stream);
+      ctx->launches += 1;
+    } else if (timing) {
+      cudaEventRecord(mb.tev[GT_VIEWWAIT], ctx->stream);
+    }
+    if (timing) cudaEventRecord(mb.tev[GT_RASTER], ctx->stream);
+  }
+  if (G > 1) {
+    size_t off[GS_GROUP_MAX_GPUS], cnt[GS_GROUP_MAX_GPUS], coff[GS_GROUP_MAX_GPUS], ccnt[GS_GROUP_MAX_GPUS];
+    for (size_t i = 1; i < L; ++i) if (pitches[i] != pitches[0]) return fail(g->m[i].ctx, GS_ERR_INVALID_ARGUMENT, "members' images differ in row pitch");
+    for (uint32_t c = 0; c < G; ++c) {
+      const uint32_t y0 = min(g->bounds[c] * kTile, H), y1 = min(g->bounds[c + 1] * kTile, H);
+      off[c] = (size_t)y0 * pitches[0]; cnt[c] = (size_t)(y1 - y0) * pitches[0];
+      coff[c] = (size_t)g->bounds[c] * 4; ccnt[c] = (size_t)(g->bounds[c + 1] - g->bounds[c]) * 4;
+    }
+    if ((rc = exchange_begin(g)) || (rc = exchange_add(g, img.data(), off, cnt)) || (rc = exchange_add(g, costs.data(), coff, ccnt)) ||
+        (rc = exchange_end(g)))
+      return rc;
+  }
+  bool host_out = false;
+  for (size_t i = 0; i < L; ++i) {
+    Member &mb = g->m[i];
+    GsContext *ctx = mb.ctx;
+    GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (timing) cudaEventRecord(mb.tev[GT_IMAGE], ctx->stream);
+    GS_CUDA_TRY(ctx, cudaMemcpyAsync(mb.h_row_cost[slot], mb.d_row_cost, (size_t)rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_cost[slot], ctx->stream));
+    GsImage *rt = rts ? rts[i] : nullptr;
+    if (rt && rt->memory != GS_MEM_DEVICE) {
+      const uint32_t hp = rt->row_pitch_bytes ? rt->row_pitch_bytes : W * pix_bytes(fmt);
+      GS_CUDA_TRY(ctx, cudaMemcpy2DAsync(rt->data, hp, img[i], pitches[i], (size_t)W * pix_bytes(fmt), H, cudaMemcpyDeviceToHost, ctx->stream));
+      host_out = true;
+    }
+  }
+  g->frame++;
+  g->hist_frames++;
+  if (host_out) return gs_group_sync(g);
+  return GS_OK;
+}
+
+int gs_group_get_stats(GsGroup *g, GsGroupStats *out) {
+  if (!g || !out) return fail(nullptr, GS_ERR_INVALID_ARGUMENT, "null argument");
+  memset(out, 0, sizeof(*out));
+  Member &mb = g->m[0];
+  GS_CUDA_TRY(mb.ctx, cudaSetDevice(mb.ctx->device));
+  GS_CUDA_TRY(mb.ctx, cudaStreamSynchronize(mb.ctx->stream));
+  GS_CUDA_TRY(mb.ctx, cudaStreamSynchronize(mb.aux));
+  out->group_size = g->size;
+  out->rank = mb.rank;
+  for (uint32_t c = 0; c <= g->size; ++c) out->row_bounds[c] = g->bounds[c];
+  for (uint32_t c = 0; c < g->size; ++c) out->slab_counts[c] = g->slab_cnt[c];
+  if (g->timed) {
+    out->distances_ms = tev_ms(mb, GT_BEGIN, GT_DIST);
+    out->slab_sort_ms = tev_ms(mb, GT_DIST, GT_SORT);
+    out->order_exchange_ms = tev_ms(mb, GT_SORT, GT_ORDER);
+    out->view_ms = tev_ms(mb, GT_V0, GT_V1);
+    float bin = 0.0f;
+    if (mb.ctx->ev_valid[EV_VIEW1] && mb.ctx->ev_valid[EV_BIN1] && cudaEventElapsedTime(&bin, mb.ctx->ev[EV_VIEW1], mb.ctx->ev[EV_BIN1]) != cudaSuccess) { cudaGetLastError(); bin = 0.0f; }
+    out->bin_ms = bin;
+    out->raster_ms = tev_ms(mb, GT_VIEWWAIT, GT_RASTER) - bin;
+    out->image_exchange_ms = tev_ms(mb, GT_RASTER, GT_IMAGE);
+    out->total_ms = tev_ms(mb, GT_BEGIN, GT_IMAGE);
+  }
+  return GS_OK;
+}
+
+}  // extern "C"

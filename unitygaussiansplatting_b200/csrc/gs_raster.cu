@@ -46,20 +46,23 @@ __device__ __forceinline__ uint32_t entry_tile(uint32_t e, uint32_t r, const Par
   return ty * tilesX + x0 + col;
 }
 
-__global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ order, const uint32_t *__restrict__ rect, uint32_t n,
-                                                  Partition part, uint32_t tilesX, volatile uint32_t *status, uint32_t *ticket,
-                                                  uint32_t nblocks, uint32_t capacity, uint32_t *__restrict__ keys,
+__global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ order, const uint32_t *__restrict__ rect,
+                                                  const uint32_t *__restrict__ d_n, Partition part, uint32_t tilesX, volatile uint32_t *status,
+                                                  uint32_t *ticket, uint32_t capacity, uint32_t *__restrict__ keys,
                                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ entry_count,
                                                   uint32_t *__restrict__ ghist, uint32_t digit_bits, bool two_pass) {
   __shared__ uint32_t s_w[8];
   __shared__ uint32_t s_block, s_excl;
   __shared__ uint32_t s_dh[512];   // digit histograms of the two sort passes over the tile ids we emit
+  const uint32_t n = __ldg(d_n);   // length of the (compacted) draw list: known on the device only
+  const uint32_t nblocks = n ? (n + kBinBlock - 1) / kBinBlock : 1u;   // an empty list still needs one block to report 0 entries
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
   s_dh[threadIdx.x] = 0; s_dh[threadIdx.x + 256] = 0;
   const uint32_t dmask = (1u << digit_bits) - 1u;
   __syncthreads();
   const uint32_t b = s_block;
+  if (b >= nblocks) return;   // the grid is sized for the whole asset; the list is usually much shorter
   // warp-striped ranks: item i of lane l is rank wbase + i*32 + l (coalesced loads, and the 32 lanes of one
   // item slot hold 32 consecutive ranks == one contiguous output range)
   const uint32_t wbase = b * kBinBlock + warp * (32 * kBinItems) + lane;
@@ -109,17 +112,18 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
         const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;   // nearest predecessor that is already inclusive
         uint32_t contrib = ((int)lane <= first) ? (v & kBinValMask) : 0u;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        excl += contrib;
+        for (int o = 16; o; o >>= 1) contrib = min(contrib + __shfl_xor_sync(0xffffffffu, contrib, o), (uint32_t)kBinValMask);
+        excl = min(excl + contrib, (uint32_t)kBinValMask);
         if (incl_mask) break;
         top -= 32;
       }
-      if (lane == 0) status[b] = kBinFlagIncl | ((excl + total) & kBinValMask);
+      // prefixes saturate instead of wrapping at 2^30: a saturated total is > any capacity, so it is reported as overflow
+      if (lane == 0) status[b] = kBinFlagIncl | min(excl + total, (uint32_t)kBinValMask);
     }
     if (lane == 0) {
       s_excl = excl;
       if (b == nblocks - 1) {
-        const uint32_t all = excl + total;
+        const uint32_t all = min(excl + total, (uint32_t)kBinValMask);
         entry_count[1] = all > capacity ? 1u : 0u;   // overflow: lists are truncated, the API reports it
         entry_count[0] = all > capacity ? capacity : all;
         entry_count[2] = all;
@@ -171,20 +175,25 @@ static void bin_sort_plan(uint32_t bins, int *bits, int *passes) {
 }
 
 BinScratch launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
-                          const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *sort_passes) {
+                          const uint32_t *draw_mask, const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *launches) {
   const Partition part = make_partition(opt);
   const uint32_t tiles = fc.binsX * fc.binsY;
-  if (sort_passes) *sort_passes = 0;
+  if (launches) *launches = 0;
   if (!n) { cudaMemsetAsync(bs.entry_count, 0, 16, s); return bs; }
+  // 1. the drawable splats in draw order: the walk over all n order slots touches only a bit mask (n/8 bytes), so the
+  //    rectangle gathers, the scan chain and the emission below run over the drawables alone (30 % of cfg2; 1/G of that per
+  //    GPU of a group)
+  launch_compact_order(order, n, draw_mask, nullptr, bs.list_ids, nullptr, bs.cmp_status, bs.entry_count + 3, s);
   const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
   cudaMemsetAsync(bs.block_sums, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
   int bits, passes;
   bin_sort_plan(tiles, &bits, &passes);
-  if (sort_passes) *sort_passes = passes;
+  if (launches) *launches = 3 + passes;   // compact, bin_emit, zero_rows, sort passes
   cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
-  k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, n, part, fc.binsX, bs.block_sums + 1, bs.block_sums, nblocks, bs.capacity,
+  k_bin_emit<<<nblocks, 256, 0, s>>>(bs.list_ids, rect, bs.entry_count + 3, part, fc.binsX, bs.block_sums + 1, bs.block_sums, bs.capacity,
                                      bs.tile_keys, bs.tile_vals, bs.entry_count, sc.ghist, (uint32_t)bits, passes == 2);
-  launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, passes, bits, true, sc, s);
+  launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, passes, bits, true, sc, s, nullptr, nullptr,
+                    /*count_is_capacity=*/false);
   BinScratch sorted = bs;   // an odd number of passes leaves the sorted lists in the sorter's ping-pong buffers
   if (passes & 1) { sorted.tile_keys = sc.alt_keys; sorted.tile_vals = sc.alt_vals; }
   return sorted;
@@ -230,7 +239,10 @@ __global__ void __launch_bounds__(256) k_bin_ranges(const uint32_t *__restrict__
 
 // Launch order of the raster tiles: longest-processing-time first, from the cost each tile measured last frame
 // (counting sort over 64 log-scale buckets, one CTA).  Pixels do not depend on the order; only the tail does.
-__global__ void __launch_bounds__(1024) k_tile_order(const uint32_t *__restrict__ cost, uint32_t ntiles, uint32_t *__restrict__ order) {
+__global__ void __launch_bounds__(1024) k_tile_order(const uint32_t *__restrict__ cost, uint32_t ntiles, uint32_t ntx, Partition part,
+                                                     uint32_t *__restrict__ order) {
+  // `cost` is indexed by the tile's id in the whole image (ty * ntx + tx) so that a moving partition keeps its history;
+  // `order` receives the ids of OUR ntiles tiles (own tile row k = kth_own_tile_row(k)), most expensive first
   __shared__ uint32_t s_hist[64], s_base[64];
   __shared__ uint32_t s_any;
   if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
@@ -242,8 +254,9 @@ __global__ void __launch_bounds__(1024) k_tile_order(const uint32_t *__restrict_
     const uint32_t half = l ? ((c >> (l - 1)) & 1u) : 0u;
     return min(63u, 1u + 2u * l + half);
   };
+  auto global_id = [&](uint32_t t) -> uint32_t { const uint32_t k = t / ntx; return part.kth_own_tile_row(k) * ntx + (t - k * ntx); };
   for (uint32_t t = threadIdx.x; t < ntiles; t += 1024) {
-    const uint32_t c = cost[t];
+    const uint32_t c = cost[global_id(t)];
     if (c) s_any = 1;
     atomicAdd(&s_hist[63u - bucket(c)], 1u);
   }
@@ -254,10 +267,28 @@ __global__ void __launch_bounds__(1024) k_tile_order(const uint32_t *__restrict_
   }
   __syncthreads();
   if (!s_any) {   // no history (first frame / new resolution): a stride permutation spreads spatial clusters
-    for (uint32_t t = threadIdx.x; t < ntiles; t += 1024) order[t] = (ntiles % 1031u) ? (uint32_t)(((uint64_t)t * 1031u) % ntiles) : t;
+    for (uint32_t t = threadIdx.x; t < ntiles; t += 1024) order[t] = global_id((ntiles % 1031u) ? (uint32_t)(((uint64_t)t * 1031u) % ntiles) : t);
     return;
   }
-  for (uint32_t t = threadIdx.x; t < ntiles; t += 1024) order[atomicAdd(&s_base[63u - bucket(cost[t])], 1u)] = t;
+  for (uint32_t t = threadIdx.x; t < ntiles; t += 1024) {
+    const uint32_t gid = global_id(t);
+    order[atomicAdd(&s_base[63u - bucket(cost[gid])], 1u)] = gid;
+  }
+}
+
+// per raster-tile row: the sum of its tiles' costs (what the group path balances its row ranges with)
+__global__ void __launch_bounds__(256) k_row_costs(const uint32_t *__restrict__ cost, uint32_t ntx, uint32_t t0, uint32_t t1,
+                                                   uint32_t *__restrict__ row_cost) {
+  const uint32_t row = t0 + blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= t1) return;
+  uint32_t acc = 0;
+  for (uint32_t x = lane; x < ntx; x += 32) acc += cost[row * ntx + x];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) row_cost[row] = acc;
+}
+void launch_row_costs(const uint32_t *cost, uint32_t ntx, uint32_t t0, uint32_t t1, uint32_t *row_cost, cudaStream_t s) {
+  if (t1 > t0) k_row_costs<<<(t1 - t0 + 7) / 8, 256, 0, s>>>(cost, ntx, t0, t1, row_cost);
 }
 
 // ---- TMA (bulk async copy) staging: one 48-byte cp.async.bulk per record, completion counted in bytes on an mbarrier ----
@@ -289,7 +320,7 @@ template <bool FP16_ROP, int OUT_FMT, bool STATS, bool TMA>
 __global__ void __launch_bounds__(256)
 k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const uint2 *__restrict__ bin_ranges,
          const uint32_t *__restrict__ tile_vals, const uint32_t *__restrict__ tile_order, uint32_t *__restrict__ tile_cost, uint32_t ntx,
-         uint8_t *__restrict__ rt, uint32_t pitch, uint32_t band_packed, unsigned long long *stats) {
+         uint8_t *__restrict__ rt, uint32_t pitch, uint32_t band_packed, uint32_t load_rt, unsigned long long *stats) {
   uint32_t st_batches = 0, st_culls = 0, st_cand = 0, st_eval = 0, st_blend = 0;   // GS_RASTER_STATS diagnostics (per warp)
   unsigned long long st_t0 = 0;
   if (STATS) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(st_t0));
@@ -313,9 +344,9 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   constexpr uint32_t R = kBin / kTile;   // raster tiles per bin edge
   // launch order != raster order: CTA i takes tile order[i] (k_tile_order: most expensive first, by last frame's cost),
   // so the expensive tiles start early instead of forming the tail
-  const uint32_t lin = __ldg(tile_order + blockIdx.x);
-  const uint32_t gy = lin / ntx;
-  const uint32_t tx = lin - gy * ntx, brow = part.kth_own_row(gy / R), ty = brow * R + (gy % R);
+  const uint32_t lin = __ldg(tile_order + blockIdx.x);   // tile id in the whole image: ty * ntx + tx
+  const uint32_t ty = lin / ntx;
+  const uint32_t tx = lin - ty * ntx, brow = ty / R;
   if (ty * kTile >= (uint32_t)fc.screenH) { if (threadIdx.x == 0) tile_cost[lin] = 0; return; }
   __shared__ uint32_t s_cost;
   if (threadIdx.x == 0) s_cost = 0;
@@ -328,6 +359,20 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   const bool in_image = px < (uint32_t)fc.screenW && py < (uint32_t)fc.screenH;
 
   float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;  // ClearRenderTarget(0,0,0,0), R/GaussianSplatRenderer.cs:196
+  // where this pixel lives in the target (band-packed: own bin row k of an interleaved partition -> rows [64k, 64k+64))
+  const uint32_t out_row = band_packed ? part.own_rows_below(brow) * kBin + (py - brow * kBin) : py;
+  if (load_rt && in_image) {
+    // GS_FLAG_LOAD_RT: the target was cleared once and earlier renderers of this camera already drew into it
+    // (R/GaussianSplatRenderer.cs:111-168 loops the active splat objects over ONE _GaussianSplatRT); blend under what is there
+    const uint8_t *row = rt + (size_t)out_row * pitch;
+    if (OUT_FMT == GS_PIX_RGBA16F) {
+      const uint2 v = reinterpret_cast<const uint2 *>(row)[px];
+      d0 = f16lo(v.x); d1 = f16hi(v.x); d2 = f16lo(v.y); d3 = f16hi(v.y);
+    } else {
+      const float4 v = reinterpret_cast<const float4 *>(row)[px];
+      d0 = v.x; d1 = v.y; d2 = v.z; d3 = v.w;
+    }
+  }
 
   // three-deep pipeline: splat ids of batch k+2 (register) -> records of batch k+1 (cp.async in flight) -> batch k (composited)
   auto load_id = [&](uint32_t e) -> uint32_t { return e < range.y ? __ldg(tile_vals + e) : 0xFFFFFFFFu; };
@@ -438,7 +483,6 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   }
 
   if (in_image) {
-    const uint32_t out_row = band_packed ? (gy / R) * kBin + (py - brow * kBin) : py;
     uint8_t *row = rt + (size_t)out_row * pitch;
     if (OUT_FMT == GS_PIX_RGBA16F) {
       uint2 o;
@@ -457,11 +501,11 @@ static constexpr int kRasterTmaDefault = 0;
 void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
                    uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s) {
   const Partition part = make_partition(opt);
-  const uint32_t rows = part.own_rows_below(fc.binsY);
+  const uint32_t rows = part.own_tile_rows(fc.binsY);
   if (!rows || !fc.binsX) return;
-  const uint32_t ntx = ((uint32_t)fc.screenW + kTile - 1) / kTile, ntiles = ntx * rows * (kBin / kTile);
+  const uint32_t ntx = ((uint32_t)fc.screenW + kTile - 1) / kTile, ntiles = ntx * rows;
   const uint32_t grid = ntiles;
-  k_tile_order<<<1, 1024, 0, s>>>(bs.tile_cost, ntiles, bs.tile_order);
+  k_tile_order<<<1, 1024, 0, s>>>(bs.tile_cost, ntiles, ntx, part, bs.tile_order);
   const bool rop = opt.blend_mode == GS_BLEND_FP16_ROP;
   uint8_t *out = reinterpret_cast<uint8_t *>(rt);
   // GS_RASTER_STATS=1: per-frame work counters (diagnostics; printed by tools/raster_stats.py through gs_debug_raster_stats)
@@ -475,12 +519,13 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const floa
   if (tma < 0) { const char *e = getenv("GS_RASTER_TMA"); tma = e ? (e[0] == '1') : kRasterTmaDefault; }
   const uint32_t bins = fc.binsX * fc.binsY;
   uint2 *ranges = reinterpret_cast<uint2 *>(bs.bin_ranges);
+  const uint32_t packed = part.range ? 0u : opt.band_packed, load = (opt.flags & GS_FLAG_LOAD_RT) ? 1u : 0u;
   k_bin_ranges<<<(bins + 7) / 8, 256, 0, s>>>(bs.tile_keys, bs.entry_count, bins, ranges);
 #define GS_LAUNCH_RASTER(ROP, FMT)                                                                                              \
   do {                                                                                                                         \
-    if (tma) k_raster<ROP, FMT, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
-    else if (stats) k_raster<ROP, FMT, true, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
-    else k_raster<ROP, FMT, false, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, opt.band_packed, stats); \
+    if (tma) k_raster<ROP, FMT, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
+    else if (stats) k_raster<ROP, FMT, true, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
+    else k_raster<ROP, FMT, false, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
   } while (0)
   if (rt_format == GS_PIX_RGBA16F) {
     if (rop) GS_LAUNCH_RASTER(true, GS_PIX_RGBA16F); else GS_LAUNCH_RASTER(false, GS_PIX_RGBA16F);
@@ -491,6 +536,7 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const floa
 }
 
 uint32_t partition_own_bin_rows(const GsRenderOptions &opt, uint32_t binsY) { return make_partition(opt).own_rows_below(binsY); }
+uint32_t partition_own_tile_rows(const GsRenderOptions &opt, uint32_t binsY) { return make_partition(opt).own_tile_rows(binsY); }
 
 // ---- 2b. multi-GPU epilogue: gathered band-packed targets -> one image ---------------------------
 __global__ void __launch_bounds__(256) k_unshuffle(const uint8_t *__restrict__ gathered, Partition part, uint32_t rows_pp, uint32_t px_bytes,
@@ -508,7 +554,7 @@ __global__ void __launch_bounds__(256) k_unshuffle(const uint8_t *__restrict__ g
 
 void launch_unshuffle(const void *gathered, uint32_t parts, uint32_t band, uint32_t rows_pp, uint32_t fmt, void *out, uint32_t pitch,
                       uint32_t W, uint32_t H, cudaStream_t s) {
-  Partition p;
+  Partition p{};
   p.count = parts; p.index = 0; p.band = band ? band : 1;
   dim3 grid((W + 31) / 32, (H + 7) / 8);
   k_unshuffle<<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t *>(gathered), p, rows_pp, fmt == GS_PIX_RGBA16F ? 8u : 16u,

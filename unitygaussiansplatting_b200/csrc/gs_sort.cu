@@ -113,7 +113,9 @@ __device__ __forceinline__ uint64_t gtime() { uint64_t t; asm volatile("mov.u64 
 
 // GATHER: the keys of this pass are keys_src[payload] (pass 0 of the depth sort reads the per-splat key
 // table through last frame's order, S/SplatUtilities.compute:76-81, without a separate gather pass).
-template <int BITS, bool GATHER, int THREADS>
+// PERSIST: a fixed grid whose CTAs keep taking tiles until the (device-side) count is exhausted -- for lists whose length
+// the host does not know when it launches (the binner's entry list): no capacity-sized grid of idle CTAs.
+template <int BITS, bool GATHER, int THREADS, bool PERSIST>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_onesweep(const uint32_t *__restrict__ src_k, const uint32_t *__restrict__ src_v, uint32_t *__restrict__ dst_k,
            uint32_t *__restrict__ dst_v, const uint32_t *__restrict__ d_count, int shift, const uint32_t *__restrict__ ghist,
@@ -132,14 +134,16 @@ k_onesweep(const uint32_t *__restrict__ src_k, const uint32_t *__restrict__ src_
   __shared__ uint32_t s_tile;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n = *d_count;
+  const uint32_t num_tiles = (n + kTileItems - 1) / kTileItems;
+  do {   // one tile per iteration (a single iteration unless PERSIST; every shared array written below was last read
+         // before a barrier of the previous iteration, so no extra barrier is needed between tiles)
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
   for (uint32_t d = tid; d < NB; d += kSortThreads) s_hist[d] = 0;
 #pragma unroll
   for (uint32_t d = lane; d < NB; d += 32) s_whist[warp][d] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
-  const uint32_t n = *d_count;
-  const uint32_t num_tiles = (n + kTileItems - 1) / kTileItems;
   if (tile >= num_tiles) return;
   const uint32_t tile_base = tile * kTileItems;
   GS_TRACE(0);
@@ -288,6 +292,121 @@ k_onesweep(const uint32_t *__restrict__ src_k, const uint32_t *__restrict__ src_
     dst_v[dst] = kv.y;
   }
   GS_TRACE(6);
+  } while (PERSIST);
+}
+
+// zero `per_item_words * ceil(count / items)` words, count read on the device: clears exactly the look-back rows a sort of a
+// device-sized list will use (instead of a capacity-sized cudaMemset)
+__global__ void __launch_bounds__(256) k_zero_rows(uint32_t *__restrict__ buf, const uint32_t *__restrict__ d_count, uint32_t items,
+                                                   uint32_t words_per_row, uint32_t row_stride_words, uint32_t reps, uint32_t rep_stride_words) {
+  const uint32_t rows = (*d_count + items - 1) / items;
+  const size_t per_rep = (size_t)rows * words_per_row;
+  for (size_t i = blockIdx.x * 256 + threadIdx.x; i < per_rep * reps; i += (size_t)gridDim.x * 256) {
+    const uint32_t rep = (uint32_t)(i / per_rep);
+    const size_t j = i - (size_t)rep * per_rep;
+    buf[(size_t)rep * rep_stride_words + (j / words_per_row) * row_stride_words + (j % words_per_row)] = 0u;
+  }
+}
+
+// ---- ordered compaction of a draw order by a membership mask ------------------------------------------
+// out[] = the ids of order[0..n) whose bit is set in `mask`, in the order they stand in (so a depth-sorted order stays
+// depth-sorted); WITH_KEYS also emits key_table[id] beside each id (the input of a slab's radix sort).  One status word per
+// 4096-item block, decoupled look-back 32 predecessors wide; the mask is N/8 bytes, i.e. L1/L2-resident, so the walk costs
+// one coalesced read of the order plus gathers for the kept items only.
+constexpr int kCmpItems = 16;
+constexpr int kCmpBlock = 256 * kCmpItems;
+enum : uint32_t { kCmpFlagLocal = 1u << 30, kCmpFlagIncl = 2u << 30, kCmpValMask = (1u << 30) - 1u };
+
+template <bool WITH_KEYS>
+__global__ void __launch_bounds__(256) k_compact_order(const uint32_t *__restrict__ order, uint32_t n, const uint32_t *__restrict__ mask,
+                                                       const uint32_t *__restrict__ key_table, uint32_t *__restrict__ out_ids,
+                                                       uint32_t *__restrict__ out_keys, volatile uint32_t *status, uint32_t *ticket,
+                                                       uint32_t *__restrict__ count_out) {
+  __shared__ uint32_t s_w[8];
+  __shared__ uint32_t s_block, s_excl;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t b = s_block;
+  const uint32_t nblocks = (n + kCmpBlock - 1) / kCmpBlock;
+  const uint32_t wbase = b * kCmpBlock + warp * (32 * kCmpItems) + lane;
+  uint32_t id[kCmpItems];
+#pragma unroll
+  for (int i = 0; i < kCmpItems; ++i) {
+    const uint32_t r = wbase + i * 32;
+    id[i] = (r < n) ? __ldg(order + r) : 0xFFFFFFFFu;
+  }
+  uint32_t keepbits = 0;
+#pragma unroll
+  for (int i = 0; i < kCmpItems; ++i) {
+    const bool keep = id[i] != 0xFFFFFFFFu && ((__ldg(mask + (id[i] >> 5)) >> (id[i] & 31u)) & 1u);
+    keepbits |= keep ? (1u << i) : 0u;
+  }
+  // ranks: slot i of a warp holds 32 consecutive order positions -> ballot prefix inside the slot, running sum over slots
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t pos[kCmpItems], wsum = 0;
+#pragma unroll
+  for (int i = 0; i < kCmpItems; ++i) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, (keepbits >> i) & 1u);
+    pos[i] = wsum + __popc(bal & lt);
+    wsum += __popc(bal);
+  }
+  if (lane == 0) s_w[warp] = wsum;
+  __syncthreads();
+  uint32_t woff = 0, total = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < 8; ++w) {
+    const uint32_t c = s_w[w];
+    if (w < warp) woff += c;
+    total += c;
+  }
+  if (warp == 0) {
+    if (lane == 0) status[b] = (b == 0 ? kCmpFlagIncl : kCmpFlagLocal) | total;
+    uint32_t excl = 0;
+    if (b > 0) {
+      int top = (int)b - 1;
+      while (true) {
+        const int idx = top - (int)lane;
+        uint32_t v;
+        do {
+          v = idx >= 0 ? status[idx] : (uint32_t)kCmpFlagIncl;
+        } while (__any_sync(0xffffffffu, v == 0));
+        const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v & kCmpFlagIncl) != 0);
+        const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+        uint32_t contrib = ((int)lane <= first) ? (v & kCmpValMask) : 0u;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (incl_mask) break;
+        top -= 32;
+      }
+      if (lane == 0) status[b] = kCmpFlagIncl | (excl + total);
+    }
+    if (lane == 0) {
+      s_excl = excl;
+      if (b == nblocks - 1) *count_out = excl + total;
+    }
+  }
+  __syncthreads();
+  const uint32_t base = s_excl + woff;
+#pragma unroll
+  for (int i = 0; i < kCmpItems; ++i) {
+    if ((keepbits >> i) & 1u) {
+      out_ids[base + pos[i]] = id[i];
+      if (WITH_KEYS) out_keys[base + pos[i]] = __ldg(key_table + id[i]);
+    }
+  }
+}
+
+size_t compact_status_words(uint32_t n) { return (size_t)(n + kCmpBlock - 1) / kCmpBlock + 1; }
+
+void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mask, const uint32_t *key_table, uint32_t *out_ids,
+                          uint32_t *out_keys, uint32_t *status /* compact_status_words(n) */, uint32_t *count_out, cudaStream_t s) {
+  if (!n) { cudaMemsetAsync(count_out, 0, 4, s); return; }
+  const uint32_t nblocks = (n + kCmpBlock - 1) / kCmpBlock;
+  cudaMemsetAsync(status, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
+  if (key_table) k_compact_order<true><<<nblocks, 256, 0, s>>>(order, n, mask, key_table, out_ids, out_keys, status + 1, status, count_out);
+  else k_compact_order<false><<<nblocks, 256, 0, s>>>(order, n, mask, nullptr, out_ids, nullptr, status + 1, status, count_out);
 }
 
 // optional per-tile phase trace of the first pass (debug/profiling aid): GS_SORT_TRACE=<file>
@@ -301,36 +420,49 @@ static int sort_threads() {
 }
 
 template <int BITS>
-static void launch_pass(uint32_t tiles, cudaStream_t s, const uint32_t *sk, const uint32_t *sv, uint32_t *dk, uint32_t *dv,
+static void launch_pass(uint32_t tiles, bool persist, cudaStream_t s, const uint32_t *sk, const uint32_t *sv, uint32_t *dk, uint32_t *dv,
                         const uint32_t *d_count, int shift, const uint32_t *ghist, uint32_t *lookback, uint32_t *ticket, uint64_t *trace,
                         bool gather) {
   auto go = [&](auto kern, int threads) {
     const size_t smem = (size_t)threads * kSortKPT * 8 + (size_t)(threads / 32) * (1u << BITS) * 4;
-    static thread_local const void *configured[16];
+    // the opt-in for > 48 KB dynamic shared memory is per function AND per device
+    struct Seen { const void *fn; int dev; };
+    static thread_local Seen configured[64];
     static thread_local int nconf = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
     bool seen = false;
-    for (int i = 0; i < nconf; ++i) seen |= configured[i] == (const void *)kern;
+    for (int i = 0; i < nconf; ++i) seen |= configured[i].fn == (const void *)kern && configured[i].dev == dev;
     if (!seen) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (nconf < 16) configured[nconf++] = (const void *)kern;
+      if (nconf < 64) configured[nconf++] = Seen{(const void *)kern, dev};
     }
     const uint32_t per = (uint32_t)threads * kSortKPT;
-    const uint32_t grid = (uint32_t)(((uint64_t)tiles * kSortTileItems + per - 1) / per);
+    uint32_t grid = (uint32_t)(((uint64_t)tiles * kSortTileItems + per - 1) / per);
+    if (persist) grid = min(grid, 148u * (1024u / (uint32_t)threads));
     kern<<<grid, threads, smem, s>>>(sk, sv, dk, dv, d_count, shift, ghist, lookback, ticket, trace);
   };
-  if (sort_threads() == 512) {
-    if (gather) go(k_onesweep<BITS, true, 512>, 512); else go(k_onesweep<BITS, false, 512>, 512);
+  if (persist) {
+    if (gather) go(k_onesweep<BITS, true, 256, true>, 256); else go(k_onesweep<BITS, false, 256, true>, 256);
+  } else if (sort_threads() == 512) {
+    if (gather) go(k_onesweep<BITS, true, 512, false>, 512); else go(k_onesweep<BITS, false, 512, false>, 512);
   } else {
-    if (gather) go(k_onesweep<BITS, true, 256>, 256); else go(k_onesweep<BITS, false, 256>, 256);
+    if (gather) go(k_onesweep<BITS, true, 256, false>, 256); else go(k_onesweep<BITS, false, 256, false>, 256);
   }
 }
 
 void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, uint32_t capacity, int passes, int bits,
-                       bool hist_ready, const SortScratch &sc, cudaStream_t s, cudaEvent_t *pass_events, const uint32_t *key_table) {
+                       bool hist_ready, const SortScratch &sc, cudaStream_t s, cudaEvent_t *pass_events, const uint32_t *key_table,
+                       bool count_is_capacity, uint32_t *final_keys, uint32_t *final_vals) {
   if (capacity == 0) return;
   const uint32_t tiles = (capacity + kSortTileItems - 1) / kSortTileItems;
   const uint32_t nb = 1u << bits;
-  cudaMemsetAsync(sc.lookback, 0, (size_t)tiles * nb * passes * sizeof(uint32_t), s);
+  // count_is_capacity: the host knows the exact count (depth sort, slab sort) -> exact grid, exact memset.  Otherwise the list
+  // length lives on the device only (the binner's entries): a persistent grid, and the look-back rows actually needed are
+  // cleared by a kernel that reads the count.
+  const bool persist = !count_is_capacity;
+  if (persist) k_zero_rows<<<148, 256, 0, s>>>(sc.lookback, d_count, kSortTileItems, nb, nb, (uint32_t)passes, tiles * nb);
+  else cudaMemsetAsync(sc.lookback, 0, (size_t)tiles * nb * passes * sizeof(uint32_t), s);
   cudaMemsetAsync(sc.tickets, 0, 4 * sizeof(uint32_t), s);
   if (!hist_ready) {
     cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
@@ -355,10 +487,11 @@ void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, 
     uint32_t *lb = sc.lookback + (size_t)p * tiles * nb;
     const bool gather = key_table != nullptr && p == 0;   // pass 0 reads key_table[vals[i]] instead of keys[i]
     const uint32_t *src_keys = gather ? key_table : sk;
-    if (bits == 5) launch_pass<5>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
-    else if (bits == 6) launch_pass<6>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
-    else if (bits == 7) launch_pass<7>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
-    else launch_pass<8>(tiles, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
+    if (p == passes - 1 && final_keys && final_vals) { dk = final_keys; dv = final_vals; }   // the last pass lands where the caller wants it
+    if (bits == 5) launch_pass<5>(tiles, persist, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
+    else if (bits == 6) launch_pass<6>(tiles, persist, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
+    else if (bits == 7) launch_pass<7>(tiles, persist, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
+    else launch_pass<8>(tiles, persist, s, src_keys, sv, dk, dv, d_count, bits * p, sc.ghist + 256 * p, lb, sc.tickets + p, trace, gather);
     uint32_t *t = sk; sk = dk; dk = t;
     t = sv; sv = dv; dv = t;
   }

@@ -45,12 +45,49 @@ constexpr int kDistItems = 4;  // keys per thread: 4 CONSECUTIVE splats, so Norm
 // CSCalcDistances writes key(pos[order[i]]) (S/SplatUtilities.compute:76-81); the multiset of keys -- all the
 // histograms need -- does not depend on the order, and the gather through `order` happens inside pass 0
 // of the radix sort (gs_sort.cu, GATHER), so this kernel is fully coalesced and nothing is gathered twice.
+//
+// SLABS (the group path): the sort is sharded by KEY RANGE.  The G-1 splitters are the current keys of the
+// splats that stood at the quantile positions of last frame's order (replicated data, so every GPU derives the same
+// values); splat i belongs to slab c = #{splitters <= key(i)}.  Besides the key table this kernel then writes a bit mask
+// of the splats of THIS GPU's slab, restricts the digit histograms to them, and counts #{key >= splitter j} for every j,
+// which gives every GPU the size and offset of every slab without any exchange.
+template <int MAXT>   // 0: no slabs; else the largest splitter count compiled for
 __global__ void __launch_bounds__(256) k_calc_distances(AssetView a, float4 row, uint32_t *__restrict__ key_table,
-                                                        uint32_t *__restrict__ ghist) {
+                                                        uint32_t *__restrict__ ghist, SlabArgs sl) {
   __shared__ uint32_t sh[4 * 256];
+  __shared__ uint32_t s_thr[MAXT + 1];
+  __shared__ uint32_t s_ge[MAXT + 1];
   for (int i = threadIdx.x; i < 1024; i += 256) sh[i] = 0;
+  const uint32_t nthr = MAXT ? sl.count - 1 : 0;   // number of splitters
+  if (MAXT) {
+    if (threadIdx.x < nthr) {
+      const uint32_t id = __ldg(sl.order_prev + sl.qpos[threadIdx.x]);
+      const float3 p = load_pos(a, id);
+      s_thr[threadIdx.x] = float_to_sortable_uint(fmaf(row.z, p.z, fmaf(row.y, p.y, fmaf(row.x, p.x, row.w))));
+      s_ge[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // ascending splitters (camera motion can reorder last frame's quantile splats)
+      for (uint32_t i = 1; i < nthr; ++i) {
+        const uint32_t v = s_thr[i];
+        uint32_t j = i;
+        while (j > 0 && s_thr[j - 1] > v) { s_thr[j] = s_thr[j - 1]; --j; }
+        s_thr[j] = v;
+      }
+      if (blockIdx.x == 0) for (uint32_t i = 0; i < nthr; ++i) sl.info[i] = s_thr[i];
+    }
+  }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
+  uint32_t lo = 0, hi = 0;
+  bool has_hi = false;
+  if (MAXT) {
+    if (sl.index > 0) lo = s_thr[sl.index - 1];
+    if (sl.index < nthr) { hi = s_thr[sl.index]; has_hi = true; }
+  }
+  uint32_t ge[MAXT + 1];
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) ge[j] = 0;
   // persistent CTAs: the shared histograms are flushed to the 1024 global counters once per CTA, not once per
   // 1024 splats (6M same-address L2 atomics were the whole cost of this kernel)
   for (uint32_t tile = blockIdx.x; tile * (256u * kDistItems) < a.n; tile += gridDim.x) {
@@ -93,30 +130,62 @@ __global__ void __launch_bounds__(256) k_calc_distances(AssetView a, float4 row,
     for (int it = 0; it < kDistItems; ++it)
       if (first + it < a.n) key_table[first + it] = k[it];
   }
+  uint32_t nib = 0;   // slab membership of this thread's 4 splats
 #pragma unroll
   for (int it = 0; it < kDistItems; ++it) {
     const bool live = first + it < a.n;
-    if (live) {
+    bool mine = live;
+    if (MAXT) {
+      mine = live && k[it] >= lo && (!has_hi || k[it] < hi);
+      if (mine) nib |= 1u << it;
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < MAXT; ++j) if ((uint32_t)j < nthr) ge[j] += (k[it] >= s_thr[j]) ? 1u : 0u;
+      }
+    }
+    if (mine) {
       atomicAdd(&sh[k[it] & 255u], 1u);
       atomicAdd(&sh[256 + ((k[it] >> 8) & 255u)], 1u);
     }
     // The two high digits are nearly constant inside a warp (Morton-ordered neighbours have similar depth);
     // plain atomics would serialise 32-way on one bank, so a uniform warp is counted with one add.
-    const uint32_t hi = k[it] >> 16;
-    const uint32_t hi0 = __shfl_sync(0xffffffffu, hi, 0);
-    const uint32_t livemask = __ballot_sync(0xffffffffu, live);
-    if (livemask == 0xffffffffu && __all_sync(0xffffffffu, hi == hi0)) {
+    const uint32_t hi16 = k[it] >> 16;
+    const uint32_t hi0 = __shfl_sync(0xffffffffu, hi16, 0);
+    const uint32_t minemask = __ballot_sync(0xffffffffu, mine);
+    if (minemask == 0xffffffffu && __all_sync(0xffffffffu, hi16 == hi0)) {
       if (lane == 0) { atomicAdd(&sh[512 + (hi0 & 255u)], 32u); atomicAdd(&sh[768 + (hi0 >> 8)], 32u); }
-    } else if (live) {
-      atomicAdd(&sh[512 + (hi & 255u)], 1u);
-      atomicAdd(&sh[768 + (hi >> 8)], 1u);
+    } else if (mine) {
+      atomicAdd(&sh[512 + (hi16 & 255u)], 1u);
+      atomicAdd(&sh[768 + (hi16 >> 8)], 1u);
     }
   }
+  if (MAXT) {   // 8 lanes x 4 bits = one mask word (first is a multiple of 4, 8 consecutive threads cover 32 splats)
+    uint32_t w = nib << ((lane & 7u) * 4u);
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    if ((lane & 7u) == 0 && first < a.n) sl.mask[first >> 5] = w;
+  }
   }  // tile loop
+  if (MAXT) {
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j) {
+      if ((uint32_t)j < nthr) {
+        uint32_t v = ge[j];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&s_ge[j], v);
+      }
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 1024; i += 256) {
     uint32_t c = sh[i];
     if (c) atomicAdd(&ghist[i], c);
+  }
+  if (MAXT && threadIdx.x < nthr) {
+    const uint32_t c = s_ge[threadIdx.x];
+    if (c) atomicAdd(&sl.info[kMaxSlabs + threadIdx.x], c);
   }
 }
 
@@ -217,7 +286,8 @@ __device__ __forceinline__ const uint8_t *color_texel_ptr(const AssetView &a, ui
 template <int SHFMT, bool CULL, bool BC7>
 __global__ void __launch_bounds__(256)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
-            uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out, Partition part) {
+            uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out,
+            uint32_t *__restrict__ draw_mask, Partition part) {
   __shared__ __align__(16) uint32_t s_view[256 * 10];
   __shared__ __align__(16) Chunk s_chunk;
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
@@ -268,13 +338,16 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
         sm *= sm; sm *= sm; sm *= sm;
         const float tr = fc.extentK * sm * sm / (wmin * wmin) + 0.6f;
         const float reach = 4.04f * fminf(sqrtf(2.0f * tr), 4096.0f) + 2.0f;
-        cull = (x1 + reach < 0.0f) || (x0 - reach > fc.screenW) || (y1 + reach < 0.0f) || (y0 - reach > fc.screenH);
+        // a range partition (group path) composites only its own pixel rows: everything else on the screen is some other GPU's
+        const float ylo = part.range ? (float)(part.t0 * kTile) : 0.0f, yhi = part.range ? fminf((float)(part.t1 * kTile), fc.screenH) : fc.screenH;
+        cull = (x1 + reach < 0.0f) || (x0 - reach > fc.screenW) || (y1 + reach < ylo) || (y0 - reach > yhi);
       }
       if (threadIdx.x == 0) s_cull = cull ? 1 : 0;
     }
     __syncthreads();
     if (s_cull) {
       if (idx < a.n) rect_out[idx] = kRectEmpty;
+      if (threadIdx.x < 8) draw_mask[blockIdx.x * 8 + threadIdx.x] = 0u;
       return;
     }
   }
@@ -410,7 +483,8 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
       const float reach = 4.04f * fminf(sqrtf(2.0f * tr), 4096.0f) + 2.0f;
       const float iw = 1.0f / clip.w;
       const float pcx = (clip.x * iw * 0.5f + 0.5f) * fc.screenW, pcy = (0.5f - 0.5f * clip.y * iw) * fc.screenH;
-      far_off = (pcx + reach < 0.0f) || (pcx - reach > fc.screenW) || (pcy + reach < 0.0f) || (pcy - reach > fc.screenH);
+      const float ylo = part.range ? (float)(part.t0 * kTile) : 0.0f, yhi = part.range ? fminf((float)(part.t1 * kTile), fc.screenH) : fc.screenH;
+      far_off = (pcx + reach < 0.0f) || (pcx - reach > fc.screenW) || (pcy + reach < ylo) || (pcy - reach > yhi);
     }
 
     if (!(clip.w <= 0.0f) && !far_off) {
@@ -468,7 +542,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
         SplatFootprint g0;
         // (multi-GPU: ... or only rows of other ranks' bands -- then its colour is somebody else's job)
         drawable = splat_footprint(clip, a1x, a1y, a2x, a2y, 65000.0f, fc.screenW, fc.screenH, g0) &&
-                   rect_entries(footprint_tile_rect(g0, fc), part) != 0;
+                   rect_entries(footprint_tile_rect(g0, fc, part), part) != 0;
         if (drawable) {
           load_color();
           finish_color();
@@ -509,7 +583,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
       }
       SplatFootprint fp;
       if (drawable && splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp)) {
-        rect = footprint_tile_rect(fp, fc);
+        rect = footprint_tile_rect(fp, fc, part);
         if (rect != kRectEmpty) {
           // raster-ready record (48 B): everything the per-pixel loop needs, so the compositor stages it with three
           // 16-byte async copies and no arithmetic.  Colours are the half-rounded values of the SplatViewData record.
@@ -521,6 +595,10 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
       }
     }
     rect_out[idx] = rect;
+  }
+  {  // one bit per splat: "has a bin rectangle" -- the binner walks the draw order through this mask and only touches drawables
+    const uint32_t m = __ballot_sync(0xffffffffu, rect != kRectEmpty);
+    if ((threadIdx.x & 31) == 0) draw_mask[idx >> 5] = m;
   }
 
   if (CULL) return;   // fused frame: the compositor reads the 48-byte draw records; _SplatViewData is not materialised
@@ -545,23 +623,27 @@ void launch_set_indices(uint32_t *order, uint32_t n, cudaStream_t s) {
   if (n) k_set_indices<<<(n + 255) / 256, 256, 0, s>>>(order, n);
 }
 
-void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s) {
+void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s, const SlabArgs *slabs) {
   if (!a.n) return;
   const uint32_t per = 256 * kDistItems;
   const uint32_t tiles = (a.n + per - 1) / per;
-  k_calc_distances<<<tiles < 148u * 8u ? tiles : 148u * 8u, 256, 0, s>>>(a, make_float4(fc.sort_row[0], fc.sort_row[1], fc.sort_row[2], fc.sort_row[3]),
-                                                         key_table, ghist);
+  const uint32_t grid = tiles < 148u * 8u ? tiles : 148u * 8u;
+  const float4 row = make_float4(fc.sort_row[0], fc.sort_row[1], fc.sort_row[2], fc.sort_row[3]);
+  SlabArgs none{};
+  if (!slabs || slabs->count <= 1) k_calc_distances<0><<<grid, 256, 0, s>>>(a, row, key_table, ghist, none);
+  else if (slabs->count <= 8) k_calc_distances<7><<<grid, 256, 0, s>>>(a, row, key_table, ghist, *slabs);
+  else k_calc_distances<kMaxSlabs - 1><<<grid, 256, 0, s>>>(a, row, key_table, ghist, *slabs);
 }
 
 template <bool CULL>
 static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                               uint32_t *rect, float4 *draw, const Partition &part, cudaStream_t s) {
+                               uint32_t *rect, float4 *draw, uint32_t *draw_mask, const Partition &part, cudaStream_t s) {
   const uint32_t grid = (a.n + 255) / 256;
   // BC7 colour (VeryLow preset) is a separate instantiation: the block decode must not cost the other formats registers
 #define GS_VIEW(SH)                                                                                                        \
   do {                                                                                                                    \
-    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part);  \
-    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, part);               \
+    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, draw_mask, part);  \
+    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, draw_mask, part);               \
   } while (0)
   switch (a.shFmt) {
     case 0: GS_VIEW(0); break;
@@ -574,10 +656,10 @@ static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const 
 }
 
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
-                      uint32_t *rect, float4 *draw, bool cull_undrawable, const Partition &part, cudaStream_t s) {
+                      uint32_t *rect, float4 *draw, uint32_t *draw_mask, bool cull_undrawable, const Partition &part, cudaStream_t s) {
   if (!a.n) return;
-  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, view, rect, draw, part, s);
-  else launch_calc_view_t<false>(a, fc, cutouts, deleted, view, rect, draw, part, s);
+  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, view, rect, draw, draw_mask, part, s);
+  else launch_calc_view_t<false>(a, fc, cutouts, deleted, view, rect, draw, draw_mask, part, s);
 }
 
 }  // namespace gs

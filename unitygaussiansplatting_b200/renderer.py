@@ -36,6 +36,16 @@ class GaussianSplatContext:
         self.handle = h
         self.device = device
 
+    @classmethod
+    def from_handle(cls, handle, device: int = -1):
+        """A context the library owns (the members of gs_group_create): wrapped, never destroyed from here."""
+        self = cls.__new__(cls)
+        self._lib = N.native()
+        self.handle = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+        self.device = device
+        self._borrowed = True
+        return self
+
     def sync(self):
         N.check(self.handle, self._lib.gs_sync(self.handle))
 
@@ -62,7 +72,8 @@ class GaussianSplatContext:
 
     def close(self):
         if self.handle:
-            self._lib.gs_destroy(self.handle)
+            if not getattr(self, "_borrowed", False):
+                self._lib.gs_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -211,6 +222,8 @@ class GaussianSplatRenderer:
         self.blend_mode = N.GS_BLEND_FP16_ROP
         self.partition = (0, 0, 1)   # index, count, band_rows
         self.band_packed = False
+        self.rows = (0, 0)           # contiguous partition: 16-pixel rows [begin, end) (GsRenderOptions.row_begin/row_end)
+        self.load_rt = False         # GS_FLAG_LOAD_RT: blend under what the target already holds (several renderers, one RT)
         self.async_readback = False  # host render targets are filled asynchronously (pinned memory; context.sync() completes them)
         d = asset.desc()
         h = C.c_void_p()
@@ -248,7 +261,8 @@ class GaussianSplatRenderer:
         o.blend_mode = self.blend_mode
         o.partition_index, o.partition_count, o.band_rows = self.partition
         o.band_packed = 1 if self.band_packed else 0
-        o.flags = N.GS_FLAG_ASYNC_READBACK if self.async_readback else 0
+        o.flags = (N.GS_FLAG_ASYNC_READBACK if self.async_readback else 0) | (N.GS_FLAG_LOAD_RT if self.load_rt else 0)
+        o.row_begin, o.row_end = self.rows
         return o
 
     # -- the hot path ----------------------------------------------------------------------------
@@ -270,11 +284,12 @@ class GaussianSplatRenderer:
         a, b = _image(rt, w, h), _image(camera_target, w, h)
         N.check(self.context.handle, self._lib.gs_composite(self.context.handle, C.byref(a), C.byref(b)))
 
-    def SortAndRenderSplats(self, cam: Camera, rt=None, camera_target=None):
-        """One frame: sort every m_SortNthFrame-th call (:120-121), view-calc, draw, optional composite."""
+    def SortAndRenderSplats(self, cam: Camera, rt=None, camera_target=None, fp=None):
+        """One frame: sort every m_SortNthFrame-th call (:120-121), view-calc, draw, optional composite.
+        fp: uniforms built ahead with frame_params(cam) (a host that knows its camera path); default: built here."""
         do_sort = 1 if (self.m_FrameCounter % max(1, int(self.m_SortNthFrame)) == 0) else 0
         self.m_FrameCounter += 1
-        fp, opt = self.frame_params(cam), self._options()
+        fp, opt = (self.frame_params(cam) if fp is None else fp), self._options()
         a = _image(rt, cam.pixelWidth, rt.shape[0]) if rt is not None else None
         b = _image(camera_target, cam.pixelWidth, cam.pixelHeight) if camera_target is not None else None
         N.check(self.context.handle,
