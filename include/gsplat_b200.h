@@ -95,6 +95,9 @@ typedef struct GsFrameParams {
   uint32_t reserved0;
   const GsCutout *cutouts;        /* host pointer, cutout_count entries, may be NULL */
   const uint32_t *deleted_bits;   /* host pointer, ceil(N/32) words or NULL == _SplatBitsValid 0 (:496-501) */
+  const uint32_t *selected_bits;  /* host pointer, ceil(N/32) words or NULL: the edit selection (_SplatSelectedBits, :496).  A
+                                     selected splat is drawn by the pixel shader's "selected" branch: magenta outline + tint,
+                                     opacity from the gaussian alone (S/RenderGaussianSplats.shader:63-73,87-101) */
 } GsFrameParams;
 
 typedef enum GsPixelFormat {

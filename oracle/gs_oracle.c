@@ -557,6 +557,11 @@ typedef struct DrawRec { /* per-splat constants of the draw, computed once (phas
 
 void gso_render(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t W, uint32_t H, uint32_t blend_mode,
                 float *rt, int threads) {
+  gso_render_sel(view, order, n, W, H, blend_mode, rt, threads, NULL);
+}
+
+void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t W, uint32_t H, uint32_t blend_mode,
+                    float *rt, int threads, const uint32_t *selected_bits) {
   memset(rt, 0, (size_t)W * H * 16); /* ClearRenderTarget(0,0,0,0), R/GaussianSplatRenderer.cs:196 */
   if (threads < 1) threads = 1;
   const float fW = (float)W, fH = (float)H;
@@ -571,7 +576,8 @@ void gso_render(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t
     float a1x = v->axis1[0], a1y = v->axis1[1], a2x = v->axis2[0], a2y = v->axis2[1];
     float cr = gso_f16tof32(v->color[0] >> 16), cg = gso_f16tof32(v->color[0]), cb = gso_f16tof32(v->color[1] >> 16),
           ca = gso_f16tof32(v->color[1]);          /* :48-51 */
-    if (!(ca >= 0.0f)) continue;                   /* "selected" branch needs valid edit bits: out of scope */
+    if (!(ca >= 0.0f)) continue;                   /* never produced by CSCalcViewData (opacity >= 0); NaN draws nothing */
+    if (selected_bits && (selected_bits[order[k] >> 5] & (1u << (order[k] & 31)))) ca = -1.0f; /* :63-73: o.col.a = -1 */
     /* centre in pixels: D3D viewport transform of clip.xy / clip.w */
     float ndx = v->pos[0] / v->pos[3], ndy = v->pos[1] / v->pos[3];
     float cx = fmaf(ndx, 0.5f, 0.5f) * fW, cy = fmaf(ndy, -0.5f, 0.5f) * fH;
@@ -610,11 +616,21 @@ void gso_render(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t
           float qa = fmaf(dy, i1y, dx * i1x), qb = fmaf(dy, i2y, dx * i2x);
           if (!(fabsf(qa) <= 2.0f && fabsf(qb) <= 2.0f)) continue; /* outside the quad */
           float power = -fmaf(qb, qb, qa * qa);     /* -dot(i.pos, i.pos), :81 */
-          float alpha = satf(gso_exp_neg(power) * ca); /* :82-86 */
+          float alpha = gso_exp_neg(power);         /* half alpha = exp(power), :82 */
+          float pr = cr, pg = cg, pb = cb;
+          if (ca >= 0.0f) {
+            alpha = satf(alpha * ca);               /* :83-86 */
+          } else {                                  /* "selected" splat: magenta outline, more opacity, magenta tint, :87-101 */
+            if (alpha > 7.0f / 255.0f) {
+              if (alpha < 10.0f / 255.0f) { alpha = 1.0f; pr = 1.0f; pg = 0.0f; pb = 1.0f; }
+              alpha = satf(alpha + 0.3f);
+            }
+            pr = lerpf(pr, 1.0f, 0.5f); pg = lerpf(pg, 0.0f, 0.5f); pb = lerpf(pb, 1.0f, 0.5f);
+          }
           if (alpha < 0.003921569f) continue;       /* discard, :103-104 */
           float *d = &rt[((size_t)py * W + px) * 4];
           float om = 1.0f - d[3];                   /* Blend OneMinusDstAlpha One, :11 */
-          float r0 = fmaf(cr * alpha, om, d[0]), r1 = fmaf(cg * alpha, om, d[1]), r2 = fmaf(cb * alpha, om, d[2]),
+          float r0 = fmaf(pr * alpha, om, d[0]), r1 = fmaf(pg * alpha, om, d[1]), r2 = fmaf(pb * alpha, om, d[2]),
                 r3 = fmaf(alpha, om, d[3]);
           if (blend_mode == 0) { r0 = round_h(r0); r1 = round_h(r1); r2 = round_h(r2); r3 = round_h(r3); }
           d[0] = r0; d[1] = r1; d[2] = r2; d[3] = r3;

@@ -64,6 +64,7 @@ typedef struct GsoFrame {            /* same fields as GsFrameParams (include/gs
   uint32_t cutout_count, reserved0;
   const GsoCutout *cutouts;
   const uint32_t *deleted_bits;
+  const uint32_t *selected_bits;     /* _SplatSelectedBits: read by the splat VERTEX shader, S/RenderGaussianSplats.shader:63-73 */
 } GsoFrame;
 
 typedef struct GsoSplat {            /* SplatData, S/GaussianSplatting.hlsl:209-216 */
@@ -116,6 +117,10 @@ GSO_API void gso_export_data(const GsoAsset *a, const GsoFrame *f, float *out62,
  *      blend_mode 0 (fp16 ROP) every value is exactly representable in half. ---- */
 GSO_API void gso_render(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t width, uint32_t height,
                         uint32_t blend_mode, float *rt, int threads);
+/* The same draw with the edit selection: a splat whose bit is set leaves the vertex shader with col.a = -1 (:63-73) and takes
+ * the pixel shader's "selected" branch (:87-101).  selected_bits NULL == _SplatBitsValid 0 == gso_render. */
+GSO_API void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t width, uint32_t height,
+                        uint32_t blend_mode, float *rt, int threads, const uint32_t *selected_bits);
 
 /* ---- GaussianComposite.shader:35-39, Blend SrcAlpha OneMinusSrcAlpha (:11).
  *      target: W*H*4 floats, read-modify-write; target_fp16 != 0 rounds the result to half. ---- */

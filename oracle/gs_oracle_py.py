@@ -31,7 +31,8 @@ class GsoFrame(C.Structure):
     _fields_ = [("mat_object_to_world", C.c_float * 16), ("mat_world_to_object", C.c_float * 16), ("mat_view", C.c_float * 16),
                 ("mat_proj_gpu", C.c_float * 16), ("screen_w", C.c_float), ("screen_h", C.c_float), ("cam_pos_world", C.c_float * 3),
                 ("splat_scale", C.c_float), ("opacity_scale", C.c_float), ("sh_order", C.c_uint32), ("sh_only", C.c_uint32),
-                ("cutout_count", C.c_uint32), ("reserved0", C.c_uint32), ("cutouts", C.c_void_p), ("deleted_bits", C.c_void_p)]
+                ("cutout_count", C.c_uint32), ("reserved0", C.c_uint32), ("cutouts", C.c_void_p), ("deleted_bits", C.c_void_p),
+                ("selected_bits", C.c_void_p)]
 
 
 class GsoSplat(C.Structure):
@@ -64,6 +65,8 @@ def lib():
         L.gso_calc_view.restype, L.gso_calc_view.argtypes = None, [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_void_p, C.c_int]
         L.gso_render.restype = None
         L.gso_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
+        L.gso_render_sel.restype = None
+        L.gso_render_sel.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]
         L.gso_composite.restype, L.gso_composite.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
         L.gso_max_threads.restype, L.gso_max_threads.argtypes = C.c_int, []
         L.gso_export_data.restype, L.gso_export_data.argtypes = None, [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_void_p, C.c_int]
@@ -147,11 +150,17 @@ def export_data(asset, fp=None, threads: int = 1) -> np.ndarray:
     return out
 
 
-def render(view: np.ndarray, order: np.ndarray, width: int, height: int, blend_mode: int = 0, threads: int = 1) -> np.ndarray:
+def render(view: np.ndarray, order: np.ndarray, width: int, height: int, blend_mode: int = 0, threads: int = 1,
+           selected_bits=None) -> np.ndarray:
     view = np.ascontiguousarray(view, np.uint32)
     order = np.ascontiguousarray(order, np.uint32)
     rt = np.zeros((height, width, 4), np.float32)
-    lib().gso_render(view.ctypes.data, order.ctypes.data, order.size, width, height, blend_mode, rt.ctypes.data, threads)
+    if selected_bits is None:
+        lib().gso_render(view.ctypes.data, order.ctypes.data, order.size, width, height, blend_mode, rt.ctypes.data, threads)
+    else:
+        bits = np.ascontiguousarray(selected_bits, np.uint32)
+        assert bits.size >= (view.shape[0] + 31) // 32
+        lib().gso_render_sel(view.ctypes.data, order.ctypes.data, order.size, width, height, blend_mode, rt.ctypes.data, threads, bits.ctypes.data)
     return rt
 
 
@@ -170,7 +179,9 @@ def frame(asset, fp, prev_order=None, width=None, height=None, blend_mode: int =
     sort_pairs(keys, order, threads)
     view = calc_view(asset, fp, threads)
     W, H = int(width or fp.screen_w), int(height or fp.screen_h)
-    rt = render(view, order, W, H, blend_mode, threads)
+    sel = C.cast(fp.selected_bits, C.POINTER(C.c_uint32)) if getattr(fp, "selected_bits", None) else None
+    bits = np.ctypeslib.as_array(sel, shape=((n + 31) // 32,)) if sel else None
+    rt = render(view, order, W, H, blend_mode, threads, bits)
     return {"keys": keys, "order": order, "view": view, "rt": rt}
 
 
@@ -194,6 +205,7 @@ def ref_hlsl():
         L.refhlsl_export.argtypes = [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refhlsl_vert.restype, L.refhlsl_vert.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refhlsl_frag.restype, L.refhlsl_frag.argtypes = C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        L.refhlsl_vert_sel.restype, L.refhlsl_vert_sel.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.refhlsl_pack_rotation.restype, L.refhlsl_pack_rotation.argtypes = C.c_uint32, [C.c_void_p, C.c_void_p]
         L.refhlsl_decode_rotation.restype, L.refhlsl_decode_rotation.argtypes = None, [C.c_uint32, C.c_void_p]
         _ref_hlsl = L
@@ -234,6 +246,16 @@ def ref_vert(view: np.ndarray, order: np.ndarray, inst: int, width: float, heigh
     clip, pos, col = np.zeros((4, 4), np.float32), np.zeros((4, 2), np.float32), np.zeros(4, np.float32)
     ref_hlsl().refhlsl_vert(view.ctypes.data, order.ctypes.data, inst, width, height, clip.ctypes.data, pos.ctypes.data, col.ctypes.data)
     return clip, pos, col
+
+
+def ref_vert_selected(view: np.ndarray, order: np.ndarray, inst: int, width: float, height: float, selected_bits: np.ndarray):
+    """vert with _SplatSelectedBits bound: the colour (rgba) draw instance `inst` leaves the vertex shader with."""
+    view = np.ascontiguousarray(view, np.uint32)
+    order = np.ascontiguousarray(order, np.uint32)
+    bits = np.ascontiguousarray(selected_bits, np.uint32)
+    col = np.zeros(4, np.float32)
+    ref_hlsl().refhlsl_vert_sel(view.ctypes.data, order.ctypes.data, inst, width, height, bits.ctypes.data, col.ctypes.data)
+    return col
 
 
 def ref_frag(col, pos_x: float, pos_y: float):

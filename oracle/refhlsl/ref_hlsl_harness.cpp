@@ -154,6 +154,20 @@ REF_API void refhlsl_vert(const GsoView *views, uint32_t *order, uint32_t inst, 
     for (int k = 0; k < 4; ++k) out_col[k] = o.col[k];
   }
 }
+// vert with an edit selection bound: _SplatBitsValid = 1 and _SplatSelectedBits = bits (S/RenderGaussianSplats.shader:63-73)
+REF_API void refhlsl_vert_sel(const GsoView *views, uint32_t *order, uint32_t inst, float screen_w, float screen_h, const uint32_t *selected_bits,
+                              float out_col[4]) {
+  using namespace refps;
+  _OrderBuffer.p = order;
+  _SplatViewData.p = (SplatViewData *)views;
+  _SplatSelectedBits.p = (const uint8_t *)selected_bits;
+  _SplatBitsValid = selected_bits ? 1u : 0u;
+  _ScreenParams = float4(screen_w, screen_h, 0, 0);
+  _CameraTargetTexture_TexelSize = float4(0, 0, 0, 0);
+  v2f o = vert(0, inst);
+  for (int k = 0; k < 4; ++k) out_col[k] = o.col[k];
+  _SplatBitsValid = 0;
+}
 // PackSmallest3Rotation + EncodeQuatToNorm10 (S/GaussianSplatting.hlsl:231-259,301-304): the HLSL twins of the importer's
 // C# helpers (R/GaussianUtils.cs:46-76, E/GaussianSplatAssetCreator.cs:717-725)
 REF_API uint32_t refhlsl_pack_rotation(const float q_xyzw[4], float packed[4]) {

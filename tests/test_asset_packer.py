@@ -189,6 +189,18 @@ def test_ply_reader_follows_the_importer(g, tmp_path):
     (tmp_path / "c.ply").write_text("ply\nformat ascii 1.0\nelement vertex 1\nend_header\n")
     with pytest.raises(ValueError):
         g.read_ply(tmp_path / "c.ply")
+    # a property type the importer does not know (its TypeToSize throws), and a header that promises more vertices than
+    # the file holds: rejected before anything is allocated from the untrusted count
+    good = (tmp_path / "a.ply").read_bytes()
+    (tmp_path / "d.ply").write_bytes(good.replace(b"property uchar", b"property int", 1))
+    with pytest.raises(ValueError):
+        g.read_ply(tmp_path / "d.ply")
+    (tmp_path / "e.ply").write_bytes(good.replace(b"element vertex %d" % n, b"element vertex %d" % (n * 1000000), 1))
+    with pytest.raises(ValueError):
+        g.read_ply(tmp_path / "e.ply")
+    (tmp_path / "f.ply").write_bytes(good[:-7])
+    with pytest.raises(ValueError):
+        g.read_ply(tmp_path / "f.ply")
 
 
 def test_spz_reader_follows_the_importer(g, tmp_path):

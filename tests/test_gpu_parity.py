@@ -285,3 +285,73 @@ def test_async_readback_equals_blocking(g, ctx):
     for k in range(5):
         assert np.array_equal(got[k].view(np.uint16), want[k].view(np.uint16)), "frame %d" % k
     r.Dispose()
+
+
+@pytest.mark.parametrize("device_rt", [False, True])
+def test_two_renderers_share_one_render_target(g, O, ctx, device_rt):
+    """GaussianSplatRenderSystem draws every active splat object into ONE _GaussianSplatRT, cleared once
+    (R/GaussianSplatRenderer.cs:111-168,196), nearest object first, each with its own sort.  GS_FLAG_LOAD_RT makes the
+    second object blend under the first; the oracle draws the concatenated, per-object-sorted list in one go."""
+    import torch
+    a = g.synthetic_asset(g.SCENE_CLUSTERED, 30000, 0x5EED0091, "Medium")
+    b = g.synthetic_asset(g.SCENE_CLUSTERED, 20000, 0x5EED0092, "VeryHigh")
+    cam = camera(g, 400, 300)
+    ra, rb = g.GaussianSplatRenderer(a, ctx), g.GaussianSplatRenderer(b, ctx)
+    ra.localToWorldMatrix = g.trs(position=(1.5, 0.0, 3.0)).astype(np.float32)      # further away: drawn second
+    rb.localToWorldMatrix = g.trs(position=(-1.0, 0.2, 0.5), scale=(0.7, 0.7, 0.7)).astype(np.float32)
+    rt = torch.zeros((300, 400, 4), dtype=torch.float16, device="cuda") if device_rt else np.zeros((300, 400, 4), np.float16)
+    active = g.SortAndRenderSplatsMulti([ra, rb], cam, rt)
+    assert active == [rb, ra]
+    ctx.sync()
+    got = rt.cpu().numpy() if device_rt else rt
+    views, orders, base = [], [], 0
+    for r in active:
+        fp, _keep = g.make_frame_params(cam, r.localToWorldMatrix)
+        ref = O.frame(r.m_Asset, fp, threads=O.max_threads())
+        assert np.array_equal(r.readback_order(), ref["order"])
+        views.append(ref["view"]); orders.append(ref["order"] + np.uint32(base)); base += r.splatCount
+    want = O.render(np.concatenate(views), np.concatenate(orders), 400, 300, 0, O.max_threads())
+    assert got.any()
+    assert np.array_equal(got.astype(np.float32), want)
+    # and the flag matters: drawing the second object from a cleared target gives something else
+    solo = np.zeros((300, 400, 4), np.float16)
+    ra.SortAndRenderSplats(cam, rt=solo)
+    assert not np.array_equal(solo, got)
+    ra.Dispose(); rb.Dispose()
+
+
+def test_selected_splats(g, O, ctx):
+    """_SplatSelectedBits (S/RenderGaussianSplats.shader:63-73,87-101): the fused frame, the staged draw and an emulated group of 3
+    all reproduce the oracle's picture of a scene with every 5th splat selected (plus some that are also deleted)."""
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 40000, 0x5EED0093, "Medium")
+    n = asset.splatCount
+    rng = np.random.default_rng(5)
+    sel = np.zeros((n + 31) // 32, np.uint32)
+    ids = np.arange(0, n, 5)
+    np.bitwise_or.at(sel, ids >> 5, np.uint32(1) << (ids & 31).astype(np.uint32))
+    dele = rng.integers(0, 2 ** 32, sel.size, dtype=np.uint64).astype(np.uint32) & rng.integers(0, 2 ** 32, sel.size, dtype=np.uint64).astype(np.uint32)
+    cam = camera(g, 400, 300)
+    r = g.GaussianSplatRenderer(asset, ctx)
+    r.m_SelectedBits, r.m_DeletedBits = sel, dele
+    rt = np.zeros((300, 400, 4), np.float16)
+    r.SortAndRenderSplats(cam, rt=rt)
+    fp, _keep = g.make_frame_params(cam, deleted_bits=dele, selected_bits=sel, splat_count=n)
+    ref = O.frame(asset, fp, threads=O.max_threads())
+    plain_fp, _k2 = g.make_frame_params(cam, deleted_bits=dele, splat_count=n)
+    plain = O.frame(asset, plain_fp, threads=O.max_threads())
+    assert not np.array_equal(plain["rt"], ref["rt"])
+    assert np.array_equal(rt.astype(np.float32), ref["rt"])
+    r.CalcViewData(cam)
+    assert np.array_equal(r.readback_view(), ref["view"])          # the selection does not touch _SplatViewData
+    rt2 = np.zeros_like(rt)
+    r.DrawSplats(cam, rt2)
+    assert np.array_equal(rt2, rt)
+    r.Dispose()
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    grp = GaussianSplatGroup.create(asset, [0, 0, 0], emulate=True)
+    grp.m_SelectedBits, grp.m_DeletedBits = sel, dele
+    rts = [np.zeros_like(rt) for _ in range(3)]
+    grp.SortAndRenderSplats(cam, rts=rts)
+    for i in range(3):
+        assert np.array_equal(rts[i], rt)
+    grp.close()

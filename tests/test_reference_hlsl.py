@@ -141,6 +141,47 @@ def test_draw_stages_match_the_reference_shader_code(g, R):
     assert checked > 700 and drawn > 400
 
 
+def test_selected_splat_branch_matches_the_reference_shader_code(g, R):
+    """With an edit selection bound the reference's vertex shader hands a selected splat to the pixel shader with col.a = -1
+    (S/RenderGaussianSplats.shader:63-73) and the pixel shader takes its "selected" branch (:87-101: opacity from the gaussian
+    alone, +0.3, a solid magenta ring where exp(power) is in (7/255, 10/255), magenta tint).  The oracle's draw with
+    selected_bits must give the picture the compiled reference vert + frag give."""
+    W, H = 200, 150
+    cam = camera(g, W, H, fov=50.0, pos=(0.1, 0.0, -3.0))
+    asset = one_splat(g, pos=(0.2, -0.1, 0.3), scale=(0.25, 0.08, 0.05), quat=(0.3, 0.5, -0.2, 0.78), opacity=0.02, dc0=(0.7, 0.5, 0.9), n_pad=40)
+    fp, _keep = g.make_frame_params(cam, sh_order=0)
+    view = R.calc_view(asset, fp)
+    order = np.arange(asset.splatCount, dtype=np.uint32)
+    bits = np.zeros(2, np.uint32)
+    bits[0] = 1                                                                            # splat 0 selected, the padding splats not
+    col = R.ref_vert_selected(view, order, 0, W, H, bits)
+    assert col[3] == -1.0
+    assert R.ref_vert_selected(view, order, 1, W, H, bits)[3] >= 0.0
+    plain = R.render(view, order[:1], W, H, blend_mode=1)
+    rt = R.render(view, order[:1], W, H, blend_mode=1, selected_bits=bits)
+    assert plain[..., 3].max() < 0.03 and rt[..., 3].max() == 1.0                          # opacity 0.02 alone is almost nothing
+    clip, qpos, _col = R.ref_vert(view, order, 0, W, H)
+    px = np.stack([(clip[:, 0] / clip[:, 3] * 0.5 + 0.5) * W, (0.5 - 0.5 * clip[:, 1] / clip[:, 3]) * H], 1).astype(np.float64)
+    A = np.linalg.solve(np.column_stack([px[:3], np.ones(3)]), qpos[:3].astype(np.float64))
+    checked = ring = 0
+    for y in range(H):
+        for x in range(W):
+            qx, qy = np.array([x + 0.5, y + 0.5, 1.0]) @ A
+            if abs(qx) > 2.3 or abs(qy) > 2.3:
+                assert rt[y, x, 3] == 0
+                continue
+            e = float(np.exp(-(qx * qx + qy * qy)))
+            if min(abs(abs(qx) - 2), abs(abs(qy) - 2)) < 2e-3 or min(abs(e - 1 / 255), abs(e - 7 / 255), abs(e - 10 / 255)) < 3e-5:
+                continue                                                                   # on the quad edge / one of the three thresholds
+            out, discarded = R.ref_frag(col, float(qx), float(qy))
+            inside = abs(qx) <= 2 and abs(qy) <= 2
+            want = np.zeros(4, np.float32) if (discarded or not inside) else out
+            assert np.abs(rt[y, x] - want).max() < 3e-6, (x, y, rt[y, x], want)
+            checked += 1
+            ring += int(want[3] == 1.0 and want[0] == 1.0 and want[1] == 0.0)
+    assert checked > 700 and ring > 20
+
+
 def test_rotation_packing_matches_the_reference_shader_code(g, R):
     """The importer packs rotations with C# twins of these HLSL functions; the packer (gsa_pack_smallest3 + its 10.10.10.2
     encoder, checked through a one-splat asset) must produce the same code words, and decoding must agree."""

@@ -48,7 +48,7 @@ class GsFrameParams(C.Structure):
         ("splat_scale", C.c_float), ("opacity_scale", C.c_float),
         ("sh_order", C.c_uint32), ("sh_only", C.c_uint32),
         ("cutout_count", C.c_uint32), ("reserved0", C.c_uint32),
-        ("cutouts", C.c_void_p), ("deleted_bits", C.c_void_p),
+        ("cutouts", C.c_void_p), ("deleted_bits", C.c_void_p), ("selected_bits", C.c_void_p),
     ]
 
 

@@ -500,6 +500,7 @@ struct PlyHeader {
   std::vector<std::pair<std::string, int>> attrs;  // name, size in bytes (4 float, 8 double, 1 uchar, 0 unknown)
   std::vector<bool> is_float;
   long data_offset = 0;
+  bool unsupported = false;
 };
 
 bool read_line(FILE *f, std::string &line) {
@@ -526,13 +527,21 @@ bool parse_ply_header(FILE *f, PlyHeader &h) {
     if (t0 == "element" && t1 == "vertex") h.count = atoll(c);
     if (t0 == "property") {
       const int size = t1 == "float" ? 4 : t1 == "double" ? 8 : t1 == "uchar" ? 1 : 0;
+      if (size == 0) h.unsupported = true;   // int / short / list ...: the importer's TypeToSize throws (E/Utils/PLYFileReader.cs:95-105)
       h.stride += size;
       h.attrs.push_back({t2, size});
       h.is_float.push_back(t1 == "float");
     }
   }
   h.data_offset = ftell(f);
-  return h.binary_le && h.count >= 0;
+  if (!h.binary_le || h.count < 0 || h.unsupported) return false;
+  // the vertex block the header promises must exist in the file (an untrusted count must not size an allocation)
+  const long here = h.data_offset;
+  if (fseek(f, 0, SEEK_END) != 0) return false;
+  const long end = ftell(f);
+  fseek(f, here, SEEK_SET);
+  if (end < here || (uint64_t)(end - here) < (uint64_t)h.count * (uint64_t)h.stride) return false;
+  return true;
 }
 
 const char *kSplatAttrs[62] = {
@@ -587,7 +596,15 @@ int64_t gsa_ply_write(const char *path, const float *records, uint32_t n, const 
   return ok ? count : -1;
 }
 
+static int ply_read_impl(const char *path, GsaInputSplat *out, uint32_t capacity);
 int gsa_ply_read(const char *path, GsaInputSplat *out, uint32_t capacity) {
+  try {
+    return ply_read_impl(path, out, capacity);
+  } catch (...) {   // nothing may cross the C boundary (std::bad_alloc on a huge file)
+    return -5;
+  }
+}
+static int ply_read_impl(const char *path, GsaInputSplat *out, uint32_t capacity) {
   const int64_t n = gsa_ply_vertex_count(path);
   if (n < 0) return (int)n;
   if (!out || (uint64_t)n > capacity) return -1;

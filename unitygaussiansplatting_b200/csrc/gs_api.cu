@@ -81,6 +81,7 @@ FrameConsts make_frame_consts(const GsFrameParams *fp) {
   fc.shOnly = fp->sh_only;
   fc.cutoutCount = fp->cutouts ? fp->cutout_count : 0;
   fc.bitsValid = fp->deleted_bits ? 1u : 0u;
+  fc.selValid = fp->selected_bits ? 1u : 0u;
   fc.binsX = ((uint32_t)fp->screen_w + kBin - 1) / kBin;
   fc.binsY = ((uint32_t)fp->screen_h + kBin - 1) / kBin;
   return fc;
@@ -191,6 +192,17 @@ int upload_frame_inputs(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, cu
     }
     GS_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_deleted, fp->deleted_bits, words * 4, cudaMemcpyHostToDevice, stream));
   }
+  if (fp->selected_bits) {
+    size_t words = ((size_t)as->av.n + 31) / 32;
+    if (words > ctx->selected_words) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(ctx->d_selected);
+      ctx->d_selected = nullptr;
+      GS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_selected, words * 4));
+      ctx->selected_words = words;
+    }
+    GS_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_selected, fp->selected_bits, words * 4, cudaMemcpyHostToDevice, stream));
+  }
   return GS_OK;
 }
 
@@ -205,6 +217,7 @@ int check_params(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
 }
 
 static int do_sort(GsContext *ctx, GsAsset *as, const FrameConsts &fc) {
+  GsNvtxRange nvtx("GaussianSplat.Sort");
   int rc = ensure_sort_scratch(ctx, as->av.n);
   if (rc) return rc;
   rec(ctx, EV_BEGIN);
@@ -228,11 +241,12 @@ static GsRenderOptions default_opts() {
 
 int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameConsts &fc, bool cull, const GsRenderOptions &opt,
             cudaStream_t stream) {
+  GsNvtxRange nvtx("GaussianSplat.CalcView");
   int rc = upload_frame_inputs(ctx, as, fp, stream);
   if (rc) return rc;
   const bool own = stream == ctx->stream;   // the group path runs view-calc beside the sort on a second stream and times it itself
   if (own) rec(ctx, EV_VIEW0);
-  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, as->view, as->rect, as->draw, as->draw_mask, cull, make_partition(opt), stream);
+  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, ctx->d_selected, as->view, as->rect, as->draw, as->draw_mask, cull, make_partition(opt), stream);
   if (own) rec(ctx, EV_VIEW1);
   ctx->launches += 1;
   as->view_valid = !cull;
@@ -250,6 +264,7 @@ int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameCon
 // binning + raster into a device image
 int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const GsRenderOptions &opt, void *d_rt, uint32_t pitch,
                      uint32_t fmt) {
+  GsNvtxRange nvtx("GaussianSplat.Draw");
   const uint32_t tiles = fc.binsX * fc.binsY;
   int rc = ensure_bin_scratch(ctx, as->av.n, tiles, 0);
   if (rc) return rc;
@@ -378,7 +393,7 @@ void gs_destroy(GsContext *ctx) {
   cudaFree(ctx->sort.alt_keys); cudaFree(ctx->sort.alt_vals); cudaFree(ctx->sort.lookback);
   cudaFree(ctx->sort.ghist); cudaFree(ctx->sort.tickets); cudaFree(ctx->d_scalar);
   cudaFree(ctx->bin.list_ids); cudaFree(ctx->bin.cmp_status); cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
-  cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted);
+  cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted); cudaFree(ctx->d_selected);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (int i = 0; i < 2; ++i) {
     cudaFree(ctx->rt_async[i]);
@@ -556,6 +571,7 @@ int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRend
 }
 
 static int composite_impl(GsContext *ctx, const void *d_rt, uint32_t rt_pitch, uint32_t rt_fmt, GsImage *tgt, uint32_t W, uint32_t H) {
+  GsNvtxRange nvtx("GaussianSplat.Compose");
   uint32_t tp = 0;
   int rc = image_ok(ctx, tgt, W, H, &tp);
   if (rc) return rc;

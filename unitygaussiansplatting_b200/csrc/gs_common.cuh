@@ -50,6 +50,7 @@ struct FrameConsts {
   float screenW, screenH;
   uint32_t shOrder, shOnly;
   uint32_t cutoutCount, bitsValid;
+  uint32_t selValid;       // an edit selection is bound (_SplatSelectedBits): selected splats take the pixel shader's other branch
   uint32_t binsX, binsY;   // kBin-pixel binning cells
 };
 

@@ -382,6 +382,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
 
   const bool timing = g->m[0].ctx->timing;
   g->timed = timing;
+  GsNvtxRange nvtx_frame("GaussianSplat.GroupFrame");
   // ---- phase A: distances + slab table on the context stream; view-calc on the second stream --------------------------
   for (size_t i = 0; i < L; ++i) {
     Member &mb = g->m[i];
@@ -442,6 +443,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
     for (uint32_t c = 0; c < G; ++c) g->slab_cnt[c] = g->slab_off[c + 1] - g->slab_off[c];
 
     // ---- phase C: compact my slab out of last frame's order, sort it into its place of the new order ------------------
+    GsNvtxRange nvtx_sort("GaussianSplat.Sort");
     for (size_t i = 0; i < L; ++i) {
       Member &mb = g->m[i];
       GsContext *ctx = mb.ctx;

@@ -3,7 +3,18 @@
 #pragma once
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; costs one predicted-not-taken branch per range when no tool is attached
+
 #include "gs_kernels.cuh"
+
+// Host-side ranges named as the reference's profiler markers (R/GaussianSplatRenderer.cs:20-22,287): an Nsight timeline of a
+// host using this library shows GaussianSplat.Sort / CalcView / Draw / Compose like Unity's profiler does.
+struct GsNvtxRange {
+  explicit GsNvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~GsNvtxRange() { nvtxRangePop(); }
+  GsNvtxRange(const GsNvtxRange &) = delete;
+  GsNvtxRange &operator=(const GsNvtxRange &) = delete;
+};
 
 struct GsContext;
 namespace gs {
@@ -48,6 +59,8 @@ struct GsContext {
   uint32_t cutout_cap = 0;
   uint32_t *d_deleted = nullptr;
   size_t deleted_words = 0;
+  uint32_t *d_selected = nullptr;
+  size_t selected_words = 0;
   uint32_t launches = 0;
 };
 

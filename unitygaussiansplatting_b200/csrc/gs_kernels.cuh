@@ -15,10 +15,15 @@ struct SplatFootprint {
   float ca;                  // opacity (half -> float)
 };
 
+// `selected`: the splat's bit is set in _SplatSelectedBits, so the vertex shader hands the pixel shader col.a = -1 (:63-73)
+// and the fragment's alpha comes from the gaussian alone (:87-101): the footprint is that of opacity 1, and the record
+// carries ca = -1 as the marker.
 __device__ __forceinline__ bool splat_footprint(float4 clip, float a1x, float a1y, float a2x, float a2y, float ca, float W,
-                                                float H, SplatFootprint &fp) {
+                                                float H, SplatFootprint &fp, bool selected = false) {
   if (!(clip.w > 0.0f)) return false;  // behindCam -> NaN vertex -> primitive dropped (shader :41-45)
-  if (!(ca >= 0.0f)) return false;     // "selected" branch (col.a = -1) needs valid edit bits: out of scope
+  if (!(ca >= 0.0f)) return false;     // CSCalcViewData never emits a negative opacity; NaN draws nothing
+  const float ca_rec = selected ? -1.0f : ca;
+  if (selected) ca = 1.0f;
   float ndx = __fdiv_rn(clip.x, clip.w), ndy = __fdiv_rn(clip.y, clip.w);
   float cx = fmaf(ndx, 0.5f, 0.5f) * W, cy = fmaf(ndy, -0.5f, 0.5f) * H;
   float ex = 2.0f * (fabsf(a1x) + fabsf(a2x)), ey = 2.0f * (fabsf(a1y) + fabsf(a2y));
@@ -29,7 +34,7 @@ __device__ __forceinline__ bool splat_footprint(float4 clip, float a1x, float a1
   fp.cx = cx; fp.cy = cy;
   fp.i1x = __fdiv_rn(a1x, n1); fp.i1y = __fdiv_rn(a1y, n1);
   fp.i2x = __fdiv_rn(a2x, n2); fp.i2y = __fdiv_rn(a2y, n2);
-  fp.ca = ca;
+  fp.ca = ca_rec;
   // visible part: the +-2 quad intersected with {r2 <= ln(255*ca)} (discard at alpha < 1/255)
   float r2 = fminf(__logf(ca * 255.0f) * 1.001f + 2.0e-3f, 8.0f);
   float rq = sqrtf(fmaxf(r2, 0.0f));
@@ -124,7 +129,7 @@ struct SlabArgs {
 void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s,
                            const SlabArgs *slabs = nullptr);
 // draw_mask: ceil(n / 256) * 8 words, bit i = splat i got a bin rectangle
-void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
+void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
                       uint32_t *rect, float4 *draw, uint32_t *draw_mask, bool cull_undrawable, const Partition &part, cudaStream_t s);
 
 // Radix sort (gs_sort.cu).  Scratch layout is owned by the caller (gs_api.cu).

@@ -316,7 +316,9 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <bool FP16_ROP, int OUT_FMT, bool STATS, bool TMA>
+// SEL: an edit selection is bound; records with opacity -1 are selected splats and take the pixel shader's other branch
+// (S/RenderGaussianSplats.shader:87-101).  A separate instantiation, so that frames without a selection pay nothing.
+template <bool FP16_ROP, int OUT_FMT, bool STATS, bool TMA, bool SEL = false>
 __global__ void __launch_bounds__(256)
 k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const uint2 *__restrict__ bin_ranges,
          const uint32_t *__restrict__ tile_vals, const uint32_t *__restrict__ tile_order, uint32_t *__restrict__ tile_cost, uint32_t ntx,
@@ -440,10 +442,24 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
         if (!__any_sync(0xffffffffu, inside)) continue;
         ++st_eval;
         const float power = -fmaf(qb, qb, qa * qa);                       // -dot(i.pos, i.pos) (:81)
-        const float alpha = __saturatef(exp_neg(power) * B.z);            // :82-86 (saturate: NaN -> 0, one instruction)
+        float alpha = exp_neg(power);                                     // half alpha = exp(power) (:82)
+        bool tint = false, outline = false;
+        if (SEL && B.z < 0.0f) {                                          // "selected": outline, more opacity, magenta tint (:87-101)
+          tint = true;
+          if (alpha > 7.0f / 255.0f) {
+            if (alpha < 10.0f / 255.0f) { alpha = 1.0f; outline = true; }
+            alpha = __saturatef(alpha + 0.3f);
+          }
+        } else {
+          alpha = __saturatef(alpha * B.z);                               // :83-86 (saturate: NaN -> 0, one instruction)
+        }
         if (inside && alpha >= 0.003921569f) {                            // discard below 1/255 (:103-104)
           if (STATS) ++st_blend;
-          const float4 C = s_c[j * ES];
+          float4 C = s_c[j * ES];
+          if (SEL && tint) {
+            if (outline) { C.x = 1.0f; C.y = 0.0f; C.z = 1.0f; }
+            C.x = lerpf(C.x, 1.0f, 0.5f); C.y = lerpf(C.y, 0.0f, 0.5f); C.z = lerpf(C.z, 1.0f, 0.5f);
+          }
           const float om = 1.0f - d3;                                     // Blend OneMinusDstAlpha One (:11)
           float n0 = fmaf(C.x * alpha, om, d0), n1 = fmaf(C.y * alpha, om, d1), n2 = fmaf(C.z * alpha, om, d2),
                 n3 = fmaf(alpha, om, d3);
@@ -523,7 +539,8 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const floa
   k_bin_ranges<<<(bins + 7) / 8, 256, 0, s>>>(bs.tile_keys, bs.entry_count, bins, ranges);
 #define GS_LAUNCH_RASTER(ROP, FMT)                                                                                              \
   do {                                                                                                                         \
-    if (tma) k_raster<ROP, FMT, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
+    if (fc.selValid) k_raster<ROP, FMT, false, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
+    else if (tma) k_raster<ROP, FMT, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
     else if (stats) k_raster<ROP, FMT, true, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
     else k_raster<ROP, FMT, false, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
   } while (0)

@@ -286,7 +286,7 @@ __device__ __forceinline__ const uint8_t *color_texel_ptr(const AssetView &a, ui
 template <int SHFMT, bool CULL, bool BC7>
 __global__ void __launch_bounds__(256)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
-            uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out,
+            const uint32_t *__restrict__ selected, uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out,
             uint32_t *__restrict__ draw_mask, Partition part) {
   __shared__ __align__(16) uint32_t s_view[256 * 10];
   __shared__ __align__(16) Chunk s_chunk;
@@ -322,21 +322,27 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
       const float cyp = fmaf(fc.vp[6], wz, fmaf(fc.vp[5], wy, fmaf(fc.vp[4], wx, fc.vp[7])));
       const float cwp = fmaf(fc.vp[14], wz, fmaf(fc.vp[13], wy, fmaf(fc.vp[12], wx, fc.vp[15])));
       const bool behind = cwp <= 0.0f;   // clip.w is affine in position: its sign over the box is decided at the corners
+      // view depth of the corner from the model-view matrix itself (not from clip.w: an orthographic projection has w == 1)
+      const float tzc = fmaf(fc.mv[10], bz, fmaf(fc.mv[9], by, fmaf(fc.mv[8], bx, fc.mv[11])));
       const uint32_t nb = __ballot_sync(0xffffffffu, behind) & 0xffu;
+      const uint32_t neg = __ballot_sync(0xffffffffu, tzc < 0.0f) & 0xffu;
       bool cull = nb == 0xffu;
       if (nb == 0u) {
         const float iw = 1.0f / cwp;
-        float x0 = (cxp * iw * 0.5f + 0.5f) * fc.screenW, y0 = (0.5f - 0.5f * cyp * iw) * fc.screenH, x1 = x0, y1 = y0, wmin = cwp;
+        float x0 = (cxp * iw * 0.5f + 0.5f) * fc.screenW, y0 = (0.5f - 0.5f * cyp * iw) * fc.screenH, x1 = x0, y1 = y0, zmin = fabsf(tzc);
 #pragma unroll
         for (int o = 4; o; o >>= 1) {
           x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
           y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-          wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+          zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
         }
-        // largest decoded scale in the chunk: lerp(min,max,t)^8 <= max^8 for t in [0,1]; view depth |tz| >= wmin (w = -tz)
+        // |tz| over the box is at least the smallest corner value when the corners agree in sign (tz is affine); a box that
+        // straddles tz = 0 gets no bound at all (reach = the 4096-pixel axis clamp)
+        if (neg != 0u && neg != 0xffu) zmin = 0.0f;
+        // largest decoded scale in the chunk: lerp(min,max,t)^8 <= max^8 for t in [0,1]
         float sm = fmaxf(f16hi(s_chunk.sclX), fmaxf(f16hi(s_chunk.sclY), f16hi(s_chunk.sclZ)));
         sm *= sm; sm *= sm; sm *= sm;
-        const float tr = fc.extentK * sm * sm / (wmin * wmin) + 0.6f;
+        const float tr = fc.extentK * sm * sm / (zmin * zmin) + 0.6f;
         const float reach = 4.04f * fminf(sqrtf(2.0f * tr), 4096.0f) + 2.0f;
         // a range partition (group path) composites only its own pixel rows: everything else on the screen is some other GPU's
         const float ylo = part.range ? (float)(part.t0 * kTile) : 0.0f, yhi = part.range ? fminf((float)(part.t1 * kTile), fc.screenH) : fc.screenH;
@@ -471,6 +477,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
     if (fc.cutoutCount && is_splat_cut(fc, cutouts, pos)) clip.w = 0.0f;
     vw[0] = __float_as_uint(clip.x); vw[1] = __float_as_uint(clip.y); vw[2] = __float_as_uint(clip.z); vw[3] = __float_as_uint(clip.w);
 
+    const bool is_sel = fc.selValid && ((__ldg(selected + (idx >> 5)) >> (idx & 31)) & 1u);
     bool far_off = false;
     if (CULL && clip.w > 0.0f) {
       // Cheap conservative screen-extent bound BEFORE the covariance maths: lambda1 <= trace(cov2d) <= |J|_F^2 |W|_F^2 smax^2 + 0.6
@@ -547,7 +554,8 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
           load_color();
           finish_color();
           // alpha = sat(exp_neg(..) * half(min(opacity*scale, 65000))) stays below 1/255 when the half is below 0.00392
-          drawable = __half2float(__float2half_rn(fminf(col.w * fc.opacityScale, 65000.0f))) >= 0.00392f;
+          // (a selected splat's alpha does not depend on its opacity at all)
+          drawable = is_sel || __half2float(__float2half_rn(fminf(col.w * fc.opacityScale, 65000.0f))) >= 0.00392f;
           if (drawable && fc.shOrder >= 1) shr.load(a.sh + (uint64_t)shIdx * shStride);
         }
       }
@@ -582,7 +590,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
         vw[9] = (f32tof16(res.z) << 16) | f32tof16(alpha);
       }
       SplatFootprint fp;
-      if (drawable && splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp)) {
+      if (drawable && splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp, is_sel)) {
         rect = footprint_tile_rect(fp, fc, part);
         if (rect != kRectEmpty) {
           // raster-ready record (48 B): everything the per-pixel loop needs, so the compositor stages it with three
@@ -636,14 +644,14 @@ void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *
 }
 
 template <bool CULL>
-static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
+static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
                                uint32_t *rect, float4 *draw, uint32_t *draw_mask, const Partition &part, cudaStream_t s) {
   const uint32_t grid = (a.n + 255) / 256;
   // BC7 colour (VeryLow preset) is a separate instantiation: the block decode must not cost the other formats registers
 #define GS_VIEW(SH)                                                                                                        \
   do {                                                                                                                    \
-    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, draw_mask, part);  \
-    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, view, rect, draw, draw_mask, part);               \
+    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, draw_mask, part);  \
+    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, draw_mask, part);               \
   } while (0)
   switch (a.shFmt) {
     case 0: GS_VIEW(0); break;
@@ -655,11 +663,11 @@ static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const 
 #undef GS_VIEW
 }
 
-void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, uint32_t *view,
+void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
                       uint32_t *rect, float4 *draw, uint32_t *draw_mask, bool cull_undrawable, const Partition &part, cudaStream_t s) {
   if (!a.n) return;
-  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, view, rect, draw, draw_mask, part, s);
-  else launch_calc_view_t<false>(a, fc, cutouts, deleted, view, rect, draw, draw_mask, part, s);
+  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, selected, view, rect, draw, draw_mask, part, s);
+  else launch_calc_view_t<false>(a, fc, cutouts, deleted, selected, view, rect, draw, draw_mask, part, s);
 }
 
 }  // namespace gs

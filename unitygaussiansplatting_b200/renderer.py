@@ -174,7 +174,7 @@ def cutout_array(cutouts):
 
 
 def make_frame_params(cam: Camera, localToWorld=None, splat_scale=1.0, opacity_scale=1.0, sh_order=3, sh_only=False, cutouts=None,
-                      deleted_bits=None, splat_count=0):
+                      deleted_bits=None, splat_count=0, selected_bits=None):
     """The uniforms C# binds in CalcViewData / SortPoints (R/GaussianSplatRenderer.cs:586-606,617-631).
     Returns (GsFrameParams, keepalive list for the borrowed host pointers)."""
     fp = N.GsFrameParams()
@@ -199,6 +199,11 @@ def make_frame_params(cam: Camera, localToWorld=None, splat_scale=1.0, opacity_s
         assert bits.size >= (splat_count + 31) // 32
         fp.deleted_bits = bits.ctypes.data
         keep.append(bits)
+    if selected_bits is not None:
+        bits = np.ascontiguousarray(selected_bits, np.uint32)
+        assert bits.size >= (splat_count + 31) // 32
+        fp.selected_bits = bits.ctypes.data
+        keep.append(bits)
     return fp, keep
 
 
@@ -213,12 +218,14 @@ class GaussianSplatRenderer:
         self.m_SHOrder = 3
         self.m_SHOnly = False
         self.m_SortNthFrame = 1
+        self.m_RenderOrder = 0       # R/GaussianSplatRenderer.cs:236: higher values draw first
         self.m_FrameCounter = 0
         self.localToWorldMatrix = np.eye(4, dtype=np.float32)  # transform of the GameObject
         self.localRotation = None    # xyzw / None = derived from the matrix (tr.localRotation, tr.localScale; export only)
         self.localScale = None
         self.m_Cutouts = []          # list of (4x4 matrix, type_and_flags)
         self.m_DeletedBits = None    # np.uint32[ceil(N/32)] or None
+        self.m_SelectedBits = None   # np.uint32[ceil(N/32)] or None (m_GpuEditSelected, R/GaussianSplatRenderer.cs:496)
         self.blend_mode = N.GS_BLEND_FP16_ROP
         self.partition = (0, 0, 1)   # index, count, band_rows
         self.band_packed = False
@@ -253,7 +260,7 @@ class GaussianSplatRenderer:
     # -- uniforms ------------------------------------------------------------------------------
     def frame_params(self, cam: Camera) -> N.GsFrameParams:
         fp, self._keep = make_frame_params(cam, self.localToWorldMatrix, self.m_SplatScale, self.m_OpacityScale, self.m_SHOrder,
-                                           self.m_SHOnly, self.m_Cutouts, self.m_DeletedBits, self.splatCount)
+                                           self.m_SHOnly, self.m_Cutouts, self.m_DeletedBits, self.splatCount, self.m_SelectedBits)
         return fp
 
     def _options(self) -> N.GsRenderOptions:
@@ -332,3 +339,29 @@ class GaussianSplatRenderer:
         order = np.ascontiguousarray(order, np.uint32)
         assert order.size == self.splatCount
         N.check(self.context.handle, self._lib.gs_upload_order(self._asset, order.ctypes.data))
+
+
+def GatherSplatsForCamera(renderers, cam: Camera):
+    """GaussianSplatRenderSystem.GatherSplatsForCamera (R/GaussianSplatRenderer.cs:73-105): the active splat objects in draw
+    order -- m_RenderOrder descending, then camera-space depth of the object's transform position ascending."""
+    w2c = cam.worldToCameraMatrix.astype(np.float64)
+
+    def depth(r):
+        p = np.asarray(r.localToWorldMatrix, np.float64)[:3, 3]
+        return -float((w2c @ np.r_[p, 1.0])[2])     # camTr.InverseTransformPoint(pos).z: +z forward (the view matrix looks down -z)
+    return sorted(renderers, key=lambda r: (-int(r.m_RenderOrder), depth(r)))
+
+
+def SortAndRenderSplatsMulti(renderers, cam: Camera, rt):
+    """GaussianSplatRenderSystem.SortAndRenderSplats (R/GaussianSplatRenderer.cs:108-169) for several splat objects of one
+    camera: ONE render target, cleared once (:196), every object blended under what the earlier ones left
+    (GS_FLAG_LOAD_RT from the second object on).  All renderers must live on one context."""
+    active = GatherSplatsForCamera(renderers, cam)
+    for i, r in enumerate(active):
+        keep = r.load_rt
+        r.load_rt = i > 0
+        try:
+            r.SortAndRenderSplats(cam, rt=rt)
+        finally:
+            r.load_rt = keep
+    return active
