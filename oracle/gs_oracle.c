@@ -595,16 +595,40 @@ void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint
     r->cr = cr; r->cg = cg; r->cb = cb; r->ca = ca;
     r->x0 = x0; r->x1 = x1; r->y0 = y0; r->y1 = y1;
   }
-  /* phase 2: rasterise + blend.  Each thread owns a band of rows and walks ALL splats in draw order, so the result
-     does not depend on the thread count. */
-  int bands = threads;
+  /* phase 2: rasterise + blend.  The image is cut into bands of rows; every band visits, in draw order, the records whose
+     rows reach into it (a per-band index list built by a counting pass), so the result depends neither on the thread count
+     nor on the band count, and no band walks records that cannot touch it. */
+  int bands = threads * 4;
   if ((uint32_t)bands > H) bands = (int)H;
+  if (bands < 1) bands = 1;
+  uint64_t *band_start = (uint64_t *)calloc((size_t)bands + 1, sizeof(uint64_t));
+  /* band t covers rows [H*t/bands, H*(t+1)/bands); first/last band of a record by scanning (bands is small) */
+  for (uint32_t k = 0; k < n; ++k) {
+    const DrawRec *r = &recs[k];
+    if (r->x0 >= r->x1) continue;
+    for (int t = 0; t < bands; ++t) {
+      const int32_t row0 = (int32_t)((uint64_t)H * t / bands), row1 = (int32_t)((uint64_t)H * (t + 1) / bands);
+      if (r->y0 < row1 && r->y1 > row0) band_start[t + 1]++;
+    }
+  }
+  for (int t = 0; t < bands; ++t) band_start[t + 1] += band_start[t];
+  uint32_t *band_list = (uint32_t *)malloc((size_t)(band_start[bands] ? band_start[bands] : 1) * sizeof(uint32_t));
+  uint64_t *fill = (uint64_t *)malloc((size_t)bands * sizeof(uint64_t));
+  for (int t = 0; t < bands; ++t) fill[t] = band_start[t];
+  for (uint32_t k = 0; k < n; ++k) {            /* in draw order, so every band's list is in draw order */
+    const DrawRec *r = &recs[k];
+    if (r->x0 >= r->x1) continue;
+    for (int t = 0; t < bands; ++t) {
+      const int32_t row0 = (int32_t)((uint64_t)H * t / bands), row1 = (int32_t)((uint64_t)H * (t + 1) / bands);
+      if (r->y0 < row1 && r->y1 > row0) band_list[fill[t]++] = k;
+    }
+  }
+  free(fill);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
-  for (int t = 0; t < bands * 4; ++t) {
-    const int32_t row0 = (int32_t)((uint64_t)H * t / (bands * 4)), row1 = (int32_t)((uint64_t)H * (t + 1) / (bands * 4));
-    for (uint32_t k = 0; k < n; ++k) {
-      const DrawRec *r = &recs[k];
-      if (r->x0 >= r->x1) continue;
+  for (int t = 0; t < bands; ++t) {
+    const int32_t row0 = (int32_t)((uint64_t)H * t / bands), row1 = (int32_t)((uint64_t)H * (t + 1) / bands);
+    for (uint64_t e = band_start[t]; e < band_start[t + 1]; ++e) {
+      const DrawRec *r = &recs[band_list[e]];
       const int32_t y0 = r->y0 < row0 ? row0 : r->y0, y1 = r->y1 > row1 ? row1 : r->y1;
       if (y0 >= y1) continue;
       const float cx = r->cx, cy = r->cy, i1x = r->i1x, i1y = r->i1y, i2x = r->i2x, i2y = r->i2y;
@@ -638,6 +662,8 @@ void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint
       }
     }
   }
+  free(band_list);
+  free(band_start);
   free(recs);
 }
 

@@ -129,12 +129,10 @@ static int ensure_bin_scratch(GsContext *ctx, uint32_t n, uint32_t tiles, uint32
   const uint32_t blocks = n / 1024 + 2;
   if (blocks > ctx->bin_blocks_cap) {
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.list_ids); cudaFree(ctx->bin.cmp_status);
-    ctx->bin.block_sums = ctx->bin.list_ids = ctx->bin.cmp_status = nullptr;
+    cudaFree(ctx->bin.block_sums);
+    ctx->bin.block_sums = nullptr;
     ctx->bin_blocks_cap = 0;
     GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.block_sums, (size_t)blocks * 4));
-    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.list_ids, (size_t)n * 4 + 16));
-    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->bin.cmp_status, compact_status_words(n) * 4));
     ctx->bin_blocks_cap = blocks;
   }
   if (tiles > ctx->tiles_cap) {
@@ -246,7 +244,7 @@ int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameCon
   if (rc) return rc;
   const bool own = stream == ctx->stream;   // the group path runs view-calc beside the sort on a second stream and times it itself
   if (own) rec(ctx, EV_VIEW0);
-  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, ctx->d_selected, as->view, as->rect, as->draw, as->draw_mask, cull, make_partition(opt), stream);
+  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, ctx->d_selected, as->view, as->rect, as->draw, as->block_flag, cull, make_partition(opt), stream);
   if (own) rec(ctx, EV_VIEW1);
   ctx->launches += 1;
   as->view_valid = !cull;
@@ -286,11 +284,11 @@ int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const GsRender
     }
   }
   int bin_launches = 0;
-  const BinScratch lists = launch_binning(fc, opt, as->av.n, as->order, as->rect, as->draw_mask, ctx->bin, ctx->sort, ctx->stream, &bin_launches);
+  const BinScratch lists = launch_binning(fc, opt, as->av.n, as->order, as->rect, as->block_flag, ctx->bin, ctx->sort, ctx->stream, &bin_launches);
   rec(ctx, EV_BIN1);
   launch_raster(fc, opt, as->draw, lists, d_rt, pitch, fmt, ctx->stream);
   rec(ctx, EV_RASTER1);
-  ctx->launches += bin_launches + 3;  // compaction, bin_emit, look-back clear, 1-2 sort passes; bin_ranges, tile_order, raster
+  ctx->launches += bin_launches + 3;  // bin_emit, look-back clear, 1-2 sort passes; bin_ranges, tile_order, raster
   GS_CUDA_TRY(ctx, cudaGetLastError());
   return GS_OK;
 }
@@ -392,7 +390,7 @@ void gs_destroy(GsContext *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->sort.alt_keys); cudaFree(ctx->sort.alt_vals); cudaFree(ctx->sort.lookback);
   cudaFree(ctx->sort.ghist); cudaFree(ctx->sort.tickets); cudaFree(ctx->d_scalar);
-  cudaFree(ctx->bin.list_ids); cudaFree(ctx->bin.cmp_status); cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
+  cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
   cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted); cudaFree(ctx->d_selected);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (int i = 0; i < 2; ++i) {
@@ -489,7 +487,7 @@ int gs_asset_upload(GsContext *ctx, const GsAssetDesc *d, GsAsset **out) {
       (e = cudaMalloc(&as->order, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->keys, n * 4)) != cudaSuccess ||
       (e = cudaMalloc(&as->key_table, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->draw, n * 48)) != cudaSuccess ||
       (e = cudaMalloc(&as->view, n * kViewStride + 16)) != cudaSuccess || (e = cudaMalloc(&as->rect, n * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&as->d_n, 4)) != cudaSuccess || (e = cudaMalloc(&as->draw_mask, ((n + 255) / 256) * 32 + 64)) != cudaSuccess) {
+      (e = cudaMalloc(&as->d_n, 4)) != cudaSuccess || (e = cudaMalloc(&as->block_flag, (n + 255) / 256 + 64)) != cudaSuccess) {
     gs_asset_destroy(as);
     return fail_cuda(ctx, e, "asset upload", __FILE__, __LINE__);
   }
@@ -511,7 +509,7 @@ void gs_asset_destroy(GsAsset *as) {
   if (!as) return;
   if (as->ctx) { cudaSetDevice(as->ctx->device); cudaStreamSynchronize(as->ctx->stream); }
   cudaFree(as->d_pos); cudaFree(as->d_other); cudaFree(as->d_sh); cudaFree(as->d_color); cudaFree(as->d_chunks);
-  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->draw); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n); cudaFree(as->draw_mask); cudaFree(as->slab_mask); cudaFree(as->order_tmp);
+  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->draw); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n); cudaFree(as->block_flag); cudaFree(as->slab_mask); cudaFree(as->order_tmp); cudaFree(as->slab_group_flag);
   delete as;
 }
 

@@ -124,6 +124,7 @@ int member_asset(Member &mb, GsAsset *as) {   // per-asset buffers only the grou
   const uint32_t n = as->av.n;
   if (!as->slab_mask) GS_CUDA_TRY(ctx, cudaMalloc(&as->slab_mask, ((size_t)(n + 1023) / 1024) * 128 + 64));
   if (!as->order_tmp) GS_CUDA_TRY(ctx, cudaMalloc(&as->order_tmp, (size_t)n * 4 + 16));
+  if (!as->slab_group_flag) GS_CUDA_TRY(ctx, cudaMalloc(&as->slab_group_flag, (size_t)(n + 127) / 128 + 64));
   const size_t words = compact_status_words(n);
   if (words > mb.cmp_words) {
     cudaStreamSynchronize(ctx->stream);
@@ -396,7 +397,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
     if (do_sort_flag) {
       SlabArgs sl;
       memset(&sl, 0, sizeof(sl));
-      sl.count = G; sl.index = mb.rank; sl.order_prev = as->order; sl.mask = as->slab_mask; sl.info = mb.d_info;
+      sl.count = G; sl.index = mb.rank; sl.order_prev = as->order; sl.mask = as->slab_mask; sl.group_flag = as->slab_group_flag; sl.info = mb.d_info;
       for (uint32_t j = 0; j + 1 < G; ++j) sl.qpos[j] = (uint32_t)(((uint64_t)N * (j + 1)) / G);
       GS_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sort.ghist, 0, 4 * 256 * 4, ctx->stream));
       GS_CUDA_TRY(ctx, cudaMemsetAsync(mb.d_info, 0, 2 * kMaxSlabs * 4, ctx->stream));
@@ -454,7 +455,8 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
         launch_sort_pairs(as->keys, as->order, as->d_n, N, 4, 8, true, ctx->sort, ctx->stream, nullptr, as->key_table);
         ctx->launches += 4;
       } else if (cnt) {
-        launch_compact_order(as->order, N, as->slab_mask, as->key_table, as->order_tmp, as->keys, mb.d_cmp_status, mb.d_slab_count, ctx->stream);
+        launch_compact_order(as->order, N, as->slab_mask, as->slab_group_flag, as->key_table, as->order_tmp, as->keys, mb.d_cmp_status, mb.d_slab_count,
+                             ctx->stream);
         launch_sort_pairs(as->keys, as->order_tmp, mb.d_slab_count, cnt, 4, 8, true, ctx->sort, ctx->stream, nullptr, nullptr, true,
                           as->keys + off, as->order + off);
         ctx->launches += 5;

@@ -124,13 +124,14 @@ struct SlabArgs {
   const uint32_t *order_prev;     // last frame's draw order (replicated)
   uint32_t qpos[kMaxSlabs - 1];   // positions in order_prev whose splats' current keys are the G-1 splitters
   uint32_t *mask;                 // out: bit i = splat i belongs to slab `index`
+  uint8_t *group_flag;            // out: byte j = some splat of [128 j, 128 j + 128) belongs to slab `index`
   uint32_t *info;                 // out (zeroed by the caller): [0, kMaxSlabs) ascending splitters, [kMaxSlabs, 2 kMaxSlabs) #{key >= splitter j}
 };
 void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s,
                            const SlabArgs *slabs = nullptr);
-// draw_mask: ceil(n / 256) * 8 words, bit i = splat i got a bin rectangle
+// block_flag: ceil(n / 256) bytes, byte j = some splat of [256 j, 256 j + 256) got a bin rectangle
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
-                      uint32_t *rect, float4 *draw, uint32_t *draw_mask, bool cull_undrawable, const Partition &part, cudaStream_t s);
+                      uint32_t *rect, float4 *draw, uint8_t *block_flag, bool cull_undrawable, const Partition &part, cudaStream_t s);
 
 // Radix sort (gs_sort.cu).  Scratch layout is owned by the caller (gs_api.cu).
 struct SortScratch {
@@ -151,26 +152,25 @@ size_t sort_lookback_words(uint32_t capacity, int passes);
 void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, uint32_t capacity, int passes, int bits, bool hist_ready,
                        const SortScratch &sc, cudaStream_t s, cudaEvent_t *pass_events = nullptr, const uint32_t *key_table = nullptr,
                        bool count_is_capacity = true, uint32_t *final_keys = nullptr, uint32_t *final_vals = nullptr);
-// out_ids (and out_keys = key_table[id] when key_table != nullptr) = the ids of order[0..n) whose mask bit is set, order kept;
-// *count_out = how many.  status: compact_status_words(n) words of scratch.
+// (out_ids, out_keys) = (id, key_table[id]) of the ids of order[0..n) whose mask bit is set, order kept; *count_out = how many.
+// group_flag (bytes, one per 128 ids) lets whole groups be skipped without reading their mask words.
+// status: compact_status_words(n) words of scratch.
 size_t compact_status_words(uint32_t n);
-void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mask, const uint32_t *key_table, uint32_t *out_ids,
-                          uint32_t *out_keys, uint32_t *status, uint32_t *count_out, cudaStream_t s);
+void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mask, const uint8_t *group_flag, const uint32_t *key_table,
+                          uint32_t *out_ids, uint32_t *out_keys, uint32_t *status, uint32_t *count_out, cudaStream_t s);
 
 // Binning + raster + composite (gs_raster.cu)
 struct BinScratch {
   uint32_t *block_sums;    // [0] block ticket, [1..] look-back status of the fused count+scan+emit kernel
-  uint32_t *entry_count;   // [0] = (tile,splat) entries clamped to capacity, [1] = overflow flag, [2] = unclamped total, [3] = drawable splats
+  uint32_t *entry_count;   // [0] = (tile,splat) entries clamped to capacity, [1] = overflow flag, [2] = unclamped total
   uint32_t *tile_keys, *tile_vals;  // capacity entries each
   uint32_t *bin_ranges;    // uint2 [start,end) per bin
   uint32_t *tile_cost, *tile_order;   // per raster tile: last frame's cost, this frame's launch order
-  uint32_t *list_ids;      // n: the drawable splats in draw order (compacted through the draw mask)
-  uint32_t *cmp_status;    // compact_status_words(n)
   uint32_t capacity;
 };
 // returns the scratch view whose tile_keys / tile_vals hold the bin-sorted lists (launch_raster's input)
 BinScratch launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
-                          const uint32_t *draw_mask, const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *launches);
+                          const uint8_t *block_flag, const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *launches);
 void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
                    uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s);
 extern unsigned long long *g_raster_stats;   // diagnostics, see GS_RASTER_STATS

@@ -47,22 +47,20 @@ __device__ __forceinline__ uint32_t entry_tile(uint32_t e, uint32_t r, const Par
 }
 
 __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ order, const uint32_t *__restrict__ rect,
-                                                  const uint32_t *__restrict__ d_n, Partition part, uint32_t tilesX, volatile uint32_t *status,
+                                                  const uint8_t *__restrict__ block_flag, uint32_t n, Partition part, uint32_t tilesX, volatile uint32_t *status,
                                                   uint32_t *ticket, uint32_t capacity, uint32_t *__restrict__ keys,
                                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ entry_count,
                                                   uint32_t *__restrict__ ghist, uint32_t digit_bits, bool two_pass) {
   __shared__ uint32_t s_w[8];
   __shared__ uint32_t s_block, s_excl;
   __shared__ uint32_t s_dh[512];   // digit histograms of the two sort passes over the tile ids we emit
-  const uint32_t n = __ldg(d_n);   // length of the (compacted) draw list: known on the device only
-  const uint32_t nblocks = n ? (n + kBinBlock - 1) / kBinBlock : 1u;   // an empty list still needs one block to report 0 entries
+  const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
   s_dh[threadIdx.x] = 0; s_dh[threadIdx.x + 256] = 0;
   const uint32_t dmask = (1u << digit_bits) - 1u;
   __syncthreads();
   const uint32_t b = s_block;
-  if (b >= nblocks) return;   // the grid is sized for the whole asset; the list is usually much shorter
   // warp-striped ranks: item i of lane l is rank wbase + i*32 + l (coalesced loads, and the 32 lanes of one
   // item slot hold 32 consecutive ranks == one contiguous output range)
   const uint32_t wbase = b * kBinBlock + warp * (32 * kBinItems) + lane;
@@ -73,7 +71,9 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
     id[i] = (r < n) ? __ldg(order + r) : 0xFFFFFFFFu;
   }
 #pragma unroll
-  for (int i = 0; i < kBinItems; ++i) rc[i] = (id[i] != 0xFFFFFFFFu) ? __ldg(rect + id[i]) : kRectEmpty;
+  // the rectangle of a splat is a random 4-byte gather; the view kernel's per-block flags (n/256 bytes: L1-resident) say
+  // where there is nothing to fetch
+  for (int i = 0; i < kBinItems; ++i) rc[i] = (id[i] != 0xFFFFFFFFu && __ldg(block_flag + (id[i] >> 8))) ? __ldg(rect + id[i]) : kRectEmpty;
   uint32_t wtot[kBinItems], wsum = 0;
 #pragma unroll
   for (int i = 0; i < kBinItems; ++i) {
@@ -175,23 +175,20 @@ static void bin_sort_plan(uint32_t bins, int *bits, int *passes) {
 }
 
 BinScratch launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
-                          const uint32_t *draw_mask, const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *launches) {
+                          const uint8_t *block_flag, const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *launches) {
   const Partition part = make_partition(opt);
   const uint32_t tiles = fc.binsX * fc.binsY;
   if (launches) *launches = 0;
   if (!n) { cudaMemsetAsync(bs.entry_count, 0, 16, s); return bs; }
-  // 1. the drawable splats in draw order: the walk over all n order slots touches only a bit mask (n/8 bytes), so the
-  //    rectangle gathers, the scan chain and the emission below run over the drawables alone (30 % of cfg2; 1/G of that per
-  //    GPU of a group)
-  launch_compact_order(order, n, draw_mask, nullptr, bs.list_ids, nullptr, bs.cmp_status, bs.entry_count + 3, s);
   const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
   cudaMemsetAsync(bs.block_sums, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
   int bits, passes;
   bin_sort_plan(tiles, &bits, &passes);
-  if (launches) *launches = 3 + passes;   // compact, bin_emit, zero_rows, sort passes
+  if (launches) *launches = 2 + passes;   // bin_emit, look-back clear, sort passes
   cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
-  k_bin_emit<<<nblocks, 256, 0, s>>>(bs.list_ids, rect, bs.entry_count + 3, part, fc.binsX, bs.block_sums + 1, bs.block_sums, bs.capacity,
+  k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, block_flag, n, part, fc.binsX, bs.block_sums + 1, bs.block_sums, bs.capacity,
                                      bs.tile_keys, bs.tile_vals, bs.entry_count, sc.ghist, (uint32_t)bits, passes == 2);
+  // the entry count lives on the device: a persistent grid sorts whatever it is (no capacity-sized grid or memset)
   launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, passes, bits, true, sc, s, nullptr, nullptr,
                     /*count_is_capacity=*/false);
   BinScratch sorted = bs;   // an odd number of passes leaves the sorted lists in the sorter's ping-pong buffers

@@ -309,16 +309,16 @@ __global__ void __launch_bounds__(256) k_zero_rows(uint32_t *__restrict__ buf, c
 }
 
 // ---- ordered compaction of a draw order by a membership mask ------------------------------------------
-// out[] = the ids of order[0..n) whose bit is set in `mask`, in the order they stand in (so a depth-sorted order stays
-// depth-sorted); WITH_KEYS also emits key_table[id] beside each id (the input of a slab's radix sort).  One status word per
-// 4096-item block, decoupled look-back 32 predecessors wide; the mask is N/8 bytes, i.e. L1/L2-resident, so the walk costs
-// one coalesced read of the order plus gathers for the kept items only.
+// (out_ids, out_keys) = (id, key_table[id]) of the ids of order[0..n) whose bit is set in `mask`, in the order they stand in: the
+// input of a slab's radix sort, compacted out of last frame's draw order.  One status word per 4096-item block, decoupled
+// look-back 32 predecessors wide.  The walk reads the order once (coalesced); per id it first looks at a byte per 128 ids
+// (n/128 bytes: L1-resident) and touches the mask word -- a random L2 access -- only where that group has members at all.
 constexpr int kCmpItems = 16;
 constexpr int kCmpBlock = 256 * kCmpItems;
 enum : uint32_t { kCmpFlagLocal = 1u << 30, kCmpFlagIncl = 2u << 30, kCmpValMask = (1u << 30) - 1u };
 
-template <bool WITH_KEYS>
 __global__ void __launch_bounds__(256) k_compact_order(const uint32_t *__restrict__ order, uint32_t n, const uint32_t *__restrict__ mask,
+                                                       const uint8_t *__restrict__ group_flag,
                                                        const uint32_t *__restrict__ key_table, uint32_t *__restrict__ out_ids,
                                                        uint32_t *__restrict__ out_keys, volatile uint32_t *status, uint32_t *ticket,
                                                        uint32_t *__restrict__ count_out) {
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256) k_compact_order(const uint32_t *__restric
   uint32_t keepbits = 0;
 #pragma unroll
   for (int i = 0; i < kCmpItems; ++i) {
-    const bool keep = id[i] != 0xFFFFFFFFu && ((__ldg(mask + (id[i] >> 5)) >> (id[i] & 31u)) & 1u);
+    const bool keep = id[i] != 0xFFFFFFFFu && __ldg(group_flag + (id[i] >> 7)) && ((__ldg(mask + (id[i] >> 5)) >> (id[i] & 31u)) & 1u);
     keepbits |= keep ? (1u << i) : 0u;
   }
   // ranks: slot i of a warp holds 32 consecutive order positions -> ballot prefix inside the slot, running sum over slots
@@ -393,20 +393,19 @@ __global__ void __launch_bounds__(256) k_compact_order(const uint32_t *__restric
   for (int i = 0; i < kCmpItems; ++i) {
     if ((keepbits >> i) & 1u) {
       out_ids[base + pos[i]] = id[i];
-      if (WITH_KEYS) out_keys[base + pos[i]] = __ldg(key_table + id[i]);
+      out_keys[base + pos[i]] = __ldg(key_table + id[i]);
     }
   }
 }
 
 size_t compact_status_words(uint32_t n) { return (size_t)(n + kCmpBlock - 1) / kCmpBlock + 1; }
 
-void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mask, const uint32_t *key_table, uint32_t *out_ids,
-                          uint32_t *out_keys, uint32_t *status /* compact_status_words(n) */, uint32_t *count_out, cudaStream_t s) {
+void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mask, const uint8_t *group_flag, const uint32_t *key_table,
+                          uint32_t *out_ids, uint32_t *out_keys, uint32_t *status /* compact_status_words(n) */, uint32_t *count_out, cudaStream_t s) {
   if (!n) { cudaMemsetAsync(count_out, 0, 4, s); return; }
   const uint32_t nblocks = (n + kCmpBlock - 1) / kCmpBlock;
   cudaMemsetAsync(status, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
-  if (key_table) k_compact_order<true><<<nblocks, 256, 0, s>>>(order, n, mask, key_table, out_ids, out_keys, status + 1, status, count_out);
-  else k_compact_order<false><<<nblocks, 256, 0, s>>>(order, n, mask, nullptr, out_ids, nullptr, status + 1, status, count_out);
+  k_compact_order<<<nblocks, 256, 0, s>>>(order, n, mask, group_flag, key_table, out_ids, out_keys, status + 1, status, count_out);
 }
 
 // optional per-tile phase trace of the first pass (debug/profiling aid): GS_SORT_TRACE=<file>

@@ -165,6 +165,11 @@ __global__ void __launch_bounds__(256) k_calc_distances(AssetView a, float4 row,
     w |= __shfl_xor_sync(0xffffffffu, w, 2);
     w |= __shfl_xor_sync(0xffffffffu, w, 4);
     if ((lane & 7u) == 0 && first < a.n) sl.mask[first >> 5] = w;
+    // one byte per 128 consecutive splats (= this warp's share of the tile): "somebody here belongs to my slab".  Morton-local
+    // splats lie in a narrow depth range, so most groups belong to one or two slabs and the compaction can skip the others
+    // without touching their mask words.
+    const uint32_t anyw = __ballot_sync(0xffffffffu, nib != 0);
+    if (lane == 0 && first < a.n) sl.group_flag[first >> 7] = anyw ? 1 : 0;
   }
   }  // tile loop
   if (MAXT) {
@@ -283,11 +288,13 @@ __device__ __forceinline__ const uint8_t *color_texel_ptr(const AssetView &a, ui
   return a.color + (uint64_t)ti * (a.colFmt == 0 ? 16u : a.colFmt == 1 ? 8u : 4u);
 }
 
+// The fused Norm6 kernel (the Medium preset's frame) sits at a register-allocation cliff: left alone ptxas picks 60 registers
+// (4 CTAs/SM, measured 200 us on cfg2); asked for 5 CTAs/SM it fits 48 without a spill (178 us).
 template <int SHFMT, bool CULL, bool BC7>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (CULL && SHFMT == 3 && !BC7) ? 5 : 1)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
             const uint32_t *__restrict__ selected, uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out,
-            uint32_t *__restrict__ draw_mask, Partition part) {
+            uint8_t *__restrict__ block_flag, Partition part) {
   __shared__ __align__(16) uint32_t s_view[256 * 10];
   __shared__ __align__(16) Chunk s_chunk;
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
@@ -353,7 +360,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
     __syncthreads();
     if (s_cull) {
       if (idx < a.n) rect_out[idx] = kRectEmpty;
-      if (threadIdx.x < 8) draw_mask[blockIdx.x * 8 + threadIdx.x] = 0u;
+      if (threadIdx.x == 0) block_flag[blockIdx.x] = 0;
       return;
     }
   }
@@ -477,7 +484,8 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
     if (fc.cutoutCount && is_splat_cut(fc, cutouts, pos)) clip.w = 0.0f;
     vw[0] = __float_as_uint(clip.x); vw[1] = __float_as_uint(clip.y); vw[2] = __float_as_uint(clip.z); vw[3] = __float_as_uint(clip.w);
 
-    const bool is_sel = fc.selValid && ((__ldg(selected + (idx >> 5)) >> (idx & 31)) & 1u);
+    // the splat's edit-selection bit, fetched where it is needed (kept out of the long-lived registers)
+    auto sel_bit = [&]() -> bool { return fc.selValid && ((__ldg(selected + (idx >> 5)) >> (idx & 31)) & 1u); };
     bool far_off = false;
     if (CULL && clip.w > 0.0f) {
       // Cheap conservative screen-extent bound BEFORE the covariance maths: lambda1 <= trace(cov2d) <= |J|_F^2 |W|_F^2 smax^2 + 0.6
@@ -555,7 +563,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
           finish_color();
           // alpha = sat(exp_neg(..) * half(min(opacity*scale, 65000))) stays below 1/255 when the half is below 0.00392
           // (a selected splat's alpha does not depend on its opacity at all)
-          drawable = is_sel || __half2float(__float2half_rn(fminf(col.w * fc.opacityScale, 65000.0f))) >= 0.00392f;
+          drawable = __half2float(__float2half_rn(fminf(col.w * fc.opacityScale, 65000.0f))) >= 0.00392f || sel_bit();
           if (drawable && fc.shOrder >= 1) shr.load(a.sh + (uint64_t)shIdx * shStride);
         }
       }
@@ -590,7 +598,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
         vw[9] = (f32tof16(res.z) << 16) | f32tof16(alpha);
       }
       SplatFootprint fp;
-      if (drawable && splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp, is_sel)) {
+      if (drawable && splat_footprint(clip, a1x, a1y, a2x, a2y, f16lo(vw[9]), fc.screenW, fc.screenH, fp, sel_bit())) {
         rect = footprint_tile_rect(fp, fc, part);
         if (rect != kRectEmpty) {
           // raster-ready record (48 B): everything the per-pixel loop needs, so the compositor stages it with three
@@ -604,9 +612,11 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
     }
     rect_out[idx] = rect;
   }
-  {  // one bit per splat: "has a bin rectangle" -- the binner walks the draw order through this mask and only touches drawables
-    const uint32_t m = __ballot_sync(0xffffffffu, rect != kRectEmpty);
-    if ((threadIdx.x & 31) == 0) draw_mask[idx >> 5] = m;
+  {  // one byte per 256-splat block: "some splat of this block has a bin rectangle".  The binner walks the draw order and
+     // gathers a splat's rectangle only when its block's flag is set: the flags (n/256 bytes) stay in L1, so the random
+     // 4-byte gathers are paid for blocks with something to draw only (every other GPU's blocks drop out in a group).
+    const int any = __syncthreads_or(rect != kRectEmpty);
+    if (threadIdx.x == 0) block_flag[blockIdx.x] = any ? 1 : 0;
   }
 
   if (CULL) return;   // fused frame: the compositor reads the 48-byte draw records; _SplatViewData is not materialised
@@ -645,13 +655,13 @@ void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *
 
 template <bool CULL>
 static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
-                               uint32_t *rect, float4 *draw, uint32_t *draw_mask, const Partition &part, cudaStream_t s) {
+                               uint32_t *rect, float4 *draw, uint8_t *block_flag, const Partition &part, cudaStream_t s) {
   const uint32_t grid = (a.n + 255) / 256;
   // BC7 colour (VeryLow preset) is a separate instantiation: the block decode must not cost the other formats registers
 #define GS_VIEW(SH)                                                                                                        \
   do {                                                                                                                    \
-    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, draw_mask, part);  \
-    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, draw_mask, part);               \
+    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_flag, part);  \
+    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_flag, part);               \
   } while (0)
   switch (a.shFmt) {
     case 0: GS_VIEW(0); break;
@@ -664,10 +674,10 @@ static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const 
 }
 
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
-                      uint32_t *rect, float4 *draw, uint32_t *draw_mask, bool cull_undrawable, const Partition &part, cudaStream_t s) {
+                      uint32_t *rect, float4 *draw, uint8_t *block_flag, bool cull_undrawable, const Partition &part, cudaStream_t s) {
   if (!a.n) return;
-  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, selected, view, rect, draw, draw_mask, part, s);
-  else launch_calc_view_t<false>(a, fc, cutouts, deleted, selected, view, rect, draw, draw_mask, part, s);
+  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, selected, view, rect, draw, block_flag, part, s);
+  else launch_calc_view_t<false>(a, fc, cutouts, deleted, selected, view, rect, draw, block_flag, part, s);
 }
 
 }  // namespace gs
