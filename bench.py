@@ -326,7 +326,7 @@ def main():
     import unitygaussiansplatting_b200 as g
     from unitygaussiansplatting_b200 import multigpu as MG
     n, quality, W, H, fov, seed, _ = WORKLOADS[args.workload]
-    stream = torch.cuda.Stream()
+    stream = torch.cuda.Stream(priority=-1)   # high priority: the group path's helper stream (view-calc) runs at the lowest and only fills gaps
     ctx = g.GaussianSplatContext(local, stream.cuda_stream)
     dev = torch.device("cuda", local)
     peak, peak_src = peaks()

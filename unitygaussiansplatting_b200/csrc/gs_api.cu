@@ -70,10 +70,25 @@ FrameConsts make_frame_consts(const GsFrameParams *fp) {
   fc.splatScale2 = fp->splat_scale * fp->splat_scale;
   fc.opacityScale = fp->opacity_scale;
   {
-    float w2 = 0.0f;
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) w2 += M_(mv, r, c) * M_(mv, r, c);
-    fc.extentK = fc.focal * fc.focal * (2.0f + fc.limX * fc.limX + fc.limY * fc.limY) * w2 * fc.splatScale2;
+    // Bound behind the fused kernel's cheap culls.  CalcCovariance2D (S/GaussianSplatting.hlsl:56-90): cov2d = T S T^t + 0.3 I with
+    // T = J W, J = (focal/tz) [I2 | -u], |u|^2 <= limX^2 + limY^2 (the clamp), W = MV 3x3, S = R diag(s^2) R^t splatScale^2.
+    // So lambda1 <= |J|_2^2 |W|_2^2 smax^2 splatScale^2 + 0.3 with |J|_2^2 = (focal/tz)^2 (1 + |u|^2); the quad reaches at most
+    // 2 (|a1x| + |a2x|) <= 2 sqrt(2) sqrt(2 lambda1) pixels from its centre.  |W|_2^2 is bounded by the smaller of the Frobenius
+    // norm and the Gershgorin bound of W^t W (exact for rotation x uniform scale, the usual transform).
+    double a[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, fro = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        for (int k = 0; k < 3; ++k) a[i][j] += (double)M_(mv, k, i) * (double)M_(mv, k, j);
+        fro += (double)M_(mv, i, j) * (double)M_(mv, i, j);
+      }
+    double gersh = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      double row = 0.0;
+      for (int j = 0; j < 3; ++j) row += a[i][j] < 0 ? -a[i][j] : a[i][j];
+      if (row > gersh) gersh = row;
+    }
+    const double w2 = (gersh < fro ? gersh : fro) * 1.0001;
+    fc.extentK = (float)((double)fc.focal * fc.focal * (1.0 + (double)fc.limX * fc.limX + (double)fc.limY * fc.limY) * w2 * fc.splatScale2);
   }
   fc.screenW = fp->screen_w;
   fc.screenH = fp->screen_h;
@@ -106,6 +121,7 @@ int ensure_sort_scratch(GsContext *ctx, uint32_t capacity) {
   ctx->lookback_words = sort_lookback_words(capacity, 4);
   GS_CUDA_TRY(ctx, cudaMalloc(&ctx->sort.lookback, ctx->lookback_words * 4));
   ctx->sort.max_tiles = (capacity + kSortTileItems - 1) / kSortTileItems;
+  ctx->sort.lookback_words = ctx->lookback_words;
   ctx->sort_capacity = capacity;
   return GS_OK;
 }
@@ -126,7 +142,7 @@ static int ensure_bin_scratch(GsContext *ctx, uint32_t n, uint32_t tiles, uint32
   }
   int rc = ensure_sort_scratch(ctx, ctx->bin.capacity > n ? ctx->bin.capacity : n);
   if (rc) return rc;
-  const uint32_t blocks = n / 1024 + 2;
+  const uint32_t blocks = n / 1024 + 2 < 1024u ? 1024u : n / 1024 + 2;   // the binner's ticket + range totals (<= 593 words) fit too
   if (blocks > ctx->bin_blocks_cap) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->bin.block_sums);
@@ -365,7 +381,14 @@ int gs_create(int cuda_device, void *stream_handle, GsContext **out) {
   auto init = [&]() -> int {
     GS_CUDA_TRY(ctx, cudaSetDevice(cuda_device));
     if (stream_handle) ctx->stream = (cudaStream_t)stream_handle;
-    else { GS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    else {
+      // own stream: highest priority, so that the group path's helper stream (view-calc, lowest priority) only fills what the
+      // sort / compositing chain on this stream leaves idle
+      int least = 0, greatest = 0;
+      GS_CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      GS_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, greatest));
+      ctx->own_stream = true;
+    }
     for (int i = 0; i < EV_COUNT; ++i) GS_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
     GS_CUDA_TRY(ctx, cudaMalloc(&ctx->sort.ghist, 4 * 256 * 4));
     GS_CUDA_TRY(ctx, cudaMalloc(&ctx->sort.tickets, 4 * 4));

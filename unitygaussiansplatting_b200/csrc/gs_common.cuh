@@ -46,7 +46,7 @@ struct FrameConsts {
   float sort_row[4]; // row 2 of (diag(1,1,-1)*view) * o2w  -- CSCalcDistances
   float cam_pos[3];
   float limX, limY, focal, splatScale2, opacityScale;
-  float extentK;     // focal^2 * (2 + limX^2 + limY^2) * |MV3x3|_F^2 * splatScale^2: trace(cov2d) <= extentK * smax^2 / tz^2 + 0.6
+  float extentK;     // focal^2 * (1 + limX^2 + limY^2) * |MV3x3|_2^2 * splatScale^2: lambda1(cov2d) <= extentK * smax^2 / tz^2 + 0.3
   float screenW, screenH;
   uint32_t shOrder, shOnly;
   uint32_t cutoutCount, bitsValid;
@@ -65,6 +65,11 @@ struct AssetView {     // device pointers + formats of one uploaded asset
 __host__ __device__ __forceinline__ uint32_t vec_stride(uint32_t fmt) {
   return fmt == 0 ? 12u : fmt == 1 ? 6u : fmt == 2 ? 4u : 2u;
 }
+
+// Pixels the +-2 quad of a splat can reach from its centre, given the bound `l1sq` on lambda1 of its 2-D covariance:
+// 2 (|a1x| + |a2x|) <= 2 sqrt(2) |axis1|, |axis1| = min(sqrt(2 lambda1), 4096); 2.9 instead of 2.83 and the two extra pixels
+// absorb float rounding and the slight non-orthonormality of an un-renormalised decoded rotation.
+__device__ __forceinline__ float quad_reach(float l1sq) { return 2.9f * fminf(sqrtf(2.0f * l1sq), 4096.0f) + 2.0f; }
 
 // ---- small device helpers -------------------------------------------------------------
 __device__ __forceinline__ float f16lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }

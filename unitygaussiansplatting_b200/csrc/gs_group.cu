@@ -38,7 +38,10 @@ struct Member {
   bool own_ctx = false;
   uint32_t rank = 0;
   ncclComm_t comm = nullptr;
-  cudaStream_t aux = nullptr;   // view-calc runs here, beside the sort chain
+  cudaStream_t aux = nullptr;   // view-calc runs here, beside the sort chain (lowest priority: it fills what the sort chain leaves idle)
+  cudaStream_t xfer = nullptr;  // the exchange of the composited rows runs here and overlaps the NEXT frame's sort chain
+  cudaEvent_t ev_raster = nullptr, ev_image = nullptr;   // rows composited / rows of every GPU in place (and read back)
+  bool image_pending = false;
   cudaEvent_t ev_begin = nullptr, ev_view = nullptr, ev_info = nullptr, ev_cost[2] = {nullptr, nullptr};
   cudaEvent_t ev_produced = nullptr, ev_consumed = nullptr;   // emulated exchange
   cudaEvent_t tev[GT_COUNT]{};
@@ -81,8 +84,11 @@ int fail_nccl(GsContext *ctx, ncclResult_t r, const char *what) {
 int member_init(Member &mb) {
   GsContext *ctx = mb.ctx;
   GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  GS_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&mb.aux, cudaStreamNonBlocking));
-  cudaEvent_t *evs[] = {&mb.ev_begin, &mb.ev_view, &mb.ev_info, &mb.ev_cost[0], &mb.ev_cost[1], &mb.ev_produced, &mb.ev_consumed};
+  int least = 0, greatest = 0;
+  GS_CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  GS_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&mb.aux, cudaStreamNonBlocking, least));
+  GS_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&mb.xfer, cudaStreamNonBlocking, greatest));
+  cudaEvent_t *evs[] = {&mb.ev_begin, &mb.ev_view, &mb.ev_info, &mb.ev_cost[0], &mb.ev_cost[1], &mb.ev_produced, &mb.ev_consumed, &mb.ev_raster, &mb.ev_image};
   for (cudaEvent_t *e : evs) GS_CUDA_TRY(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (int i = 0; i < GT_COUNT; ++i) GS_CUDA_TRY(ctx, cudaEventCreate(&mb.tev[i]));
   GS_CUDA_TRY(ctx, cudaMalloc(&mb.d_info, 2 * kMaxSlabs * 4));
@@ -96,7 +102,8 @@ void member_free(Member &mb) {
   cudaSetDevice(mb.ctx->device);
   cudaStreamSynchronize(mb.ctx->stream);
   if (mb.aux) { cudaStreamSynchronize(mb.aux); cudaStreamDestroy(mb.aux); }
-  cudaEvent_t evs[] = {mb.ev_begin, mb.ev_view, mb.ev_info, mb.ev_cost[0], mb.ev_cost[1], mb.ev_produced, mb.ev_consumed};
+  if (mb.xfer) { cudaStreamSynchronize(mb.xfer); cudaStreamDestroy(mb.xfer); }
+  cudaEvent_t evs[] = {mb.ev_begin, mb.ev_view, mb.ev_info, mb.ev_cost[0], mb.ev_cost[1], mb.ev_produced, mb.ev_consumed, mb.ev_raster, mb.ev_image};
   for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
   for (int i = 0; i < GT_COUNT; ++i) if (mb.tev[i]) cudaEventDestroy(mb.tev[i]);
   cudaFree(mb.d_info); cudaFree(mb.d_slab_count); cudaFree(mb.d_cmp_status); cudaFree(mb.d_row_cost); cudaFree(mb.rt_scratch);
@@ -142,8 +149,10 @@ int exchange_begin(GsGroup *g) {
   if (g->use_nccl) GS_NCCL_TRY(g->m[0].ctx, nccl_api().GroupStart());
   return GS_OK;
 }
-int exchange_add(GsGroup *g, uint8_t *const *bufs, const size_t *off, const size_t *cnt) {
+// on_xfer: use the members' transfer streams instead of their context streams
+int exchange_add(GsGroup *g, uint8_t *const *bufs, const size_t *off, const size_t *cnt, bool on_xfer = false) {
   const uint32_t G = g->size;
+  auto st = [&](Member &m) -> cudaStream_t { return on_xfer ? m.xfer : m.ctx->stream; };
   if (g->use_nccl) {
     const NcclApi &nc = nccl_api();
     for (size_t i = 0; i < g->m.size(); ++i) {
@@ -151,32 +160,32 @@ int exchange_add(GsGroup *g, uint8_t *const *bufs, const size_t *off, const size
       if (g->xfer == 1) {
         for (uint32_t p = 0; p < G; ++p) {
           if (p == mb.rank) continue;
-          if (cnt[mb.rank]) GS_NCCL_TRY(mb.ctx, nc.Send(bufs[i] + off[mb.rank], cnt[mb.rank], ncclUint8, (int)p, mb.comm, mb.ctx->stream));
-          if (cnt[p]) GS_NCCL_TRY(mb.ctx, nc.Recv(bufs[i] + off[p], cnt[p], ncclUint8, (int)p, mb.comm, mb.ctx->stream));
+          if (cnt[mb.rank]) GS_NCCL_TRY(mb.ctx, nc.Send(bufs[i] + off[mb.rank], cnt[mb.rank], ncclUint8, (int)p, mb.comm, st(mb)));
+          if (cnt[p]) GS_NCCL_TRY(mb.ctx, nc.Recv(bufs[i] + off[p], cnt[p], ncclUint8, (int)p, mb.comm, st(mb)));
         }
       } else {
         for (uint32_t c = 0; c < G; ++c)
-          if (cnt[c]) GS_NCCL_TRY(mb.ctx, nc.Broadcast(bufs[i] + off[c], bufs[i] + off[c], cnt[c], ncclUint8, (int)c, mb.comm, mb.ctx->stream));
+          if (cnt[c]) GS_NCCL_TRY(mb.ctx, nc.Broadcast(bufs[i] + off[c], bufs[i] + off[c], cnt[c], ncclUint8, (int)c, mb.comm, st(mb)));
       }
     }
     return GS_OK;
   }
   // all ranks are local members (member i == rank i): copies ordered by events, with barrier semantics like a collective
-  for (Member &mb : g->m) { cudaSetDevice(mb.ctx->device); GS_CUDA_TRY(mb.ctx, cudaEventRecord(mb.ev_produced, mb.ctx->stream)); }
+  for (Member &mb : g->m) { cudaSetDevice(mb.ctx->device); GS_CUDA_TRY(mb.ctx, cudaEventRecord(mb.ev_produced, st(mb))); }
   for (uint32_t d = 0; d < G; ++d) {
     Member &dst = g->m[d];
     cudaSetDevice(dst.ctx->device);
     for (uint32_t c = 0; c < G; ++c) {
       if (c == d || !cnt[c]) continue;
-      GS_CUDA_TRY(dst.ctx, cudaStreamWaitEvent(dst.ctx->stream, g->m[c].ev_produced, 0));
-      GS_CUDA_TRY(dst.ctx, cudaMemcpyAsync(bufs[d] + off[c], bufs[c] + off[c], cnt[c], cudaMemcpyDefault, dst.ctx->stream));
+      GS_CUDA_TRY(dst.ctx, cudaStreamWaitEvent(st(dst), g->m[c].ev_produced, 0));
+      GS_CUDA_TRY(dst.ctx, cudaMemcpyAsync(bufs[d] + off[c], bufs[c] + off[c], cnt[c], cudaMemcpyDefault, st(dst)));
     }
-    GS_CUDA_TRY(dst.ctx, cudaEventRecord(dst.ev_consumed, dst.ctx->stream));
+    GS_CUDA_TRY(dst.ctx, cudaEventRecord(dst.ev_consumed, st(dst)));
   }
   for (uint32_t c = 0; c < G; ++c) {
     cudaSetDevice(g->m[c].ctx->device);
     for (uint32_t d = 0; d < G; ++d)
-      if (d != c) GS_CUDA_TRY(g->m[c].ctx, cudaStreamWaitEvent(g->m[c].ctx->stream, g->m[d].ev_consumed, 0));
+      if (d != c) GS_CUDA_TRY(g->m[c].ctx, cudaStreamWaitEvent(st(g->m[c]), g->m[d].ev_consumed, 0));
   }
   return GS_OK;
 }
@@ -340,7 +349,9 @@ int gs_group_sync(GsGroup *g) {
   for (Member &mb : g->m) {
     cudaSetDevice(mb.ctx->device);
     cudaError_t e = cudaStreamSynchronize(mb.aux);
-    if (e != cudaSuccess && rc == GS_OK) rc = fail_cuda(mb.ctx, e, "cudaStreamSynchronize(aux)", __FILE__, __LINE__);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(mb.xfer);
+    if (e != cudaSuccess && rc == GS_OK) rc = fail_cuda(mb.ctx, e, "cudaStreamSynchronize(aux/xfer)", __FILE__, __LINE__);
+    mb.image_pending = false;
     const int r = gs_sync(mb.ctx);
     if (r != GS_OK && rc == GS_OK) rc = r;
   }
@@ -509,6 +520,8 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
     if (opt.row_end > opt.row_begin || G == 1) {
       if (G == 1) opt.row_begin = opt.row_end = 0;
       GS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, mb.ev_view, 0));
+      // the previous frame's row exchange (transfer stream) may still be filling this image: composite only after it
+      if (mb.image_pending) GS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, mb.ev_image, 0));
       if (timing) cudaEventRecord(mb.tev[GT_VIEWWAIT], ctx->stream);
       rec(ctx, EV_VIEW1);
       if ((rc = do_render(ctx, as, fc, opt, d_rt, pitch, fmt))) return rc;
@@ -519,6 +532,15 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
     }
     if (timing) cudaEventRecord(mb.tev[GT_RASTER], ctx->stream);
   }
+  // The exchange of the composited rows (and of their measured costs) goes to the transfer stream: it needs no SM to speak
+  // of, and the next frame's distance / sort chain does not depend on it, so the two overlap; the next frame's compositor
+  // waits for it (above), gs_group_sync / a host image complete it.
+  for (size_t i = 0; i < L; ++i) {
+    Member &mb = g->m[i];
+    GS_CUDA_TRY(mb.ctx, cudaSetDevice(mb.ctx->device));
+    GS_CUDA_TRY(mb.ctx, cudaEventRecord(mb.ev_raster, mb.ctx->stream));
+    GS_CUDA_TRY(mb.ctx, cudaStreamWaitEvent(mb.xfer, mb.ev_raster, 0));
+  }
   if (G > 1) {
     size_t off[GS_GROUP_MAX_GPUS], cnt[GS_GROUP_MAX_GPUS], coff[GS_GROUP_MAX_GPUS], ccnt[GS_GROUP_MAX_GPUS];
     for (size_t i = 1; i < L; ++i) if (pitches[i] != pitches[0]) return fail(g->m[i].ctx, GS_ERR_INVALID_ARGUMENT, "members' images differ in row pitch");
@@ -527,7 +549,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
       off[c] = (size_t)y0 * pitches[0]; cnt[c] = (size_t)(y1 - y0) * pitches[0];
       coff[c] = (size_t)g->bounds[c] * 4; ccnt[c] = (size_t)(g->bounds[c + 1] - g->bounds[c]) * 4;
     }
-    if ((rc = exchange_begin(g)) || (rc = exchange_add(g, img.data(), off, cnt)) || (rc = exchange_add(g, costs.data(), coff, ccnt)) ||
+    if ((rc = exchange_begin(g)) || (rc = exchange_add(g, img.data(), off, cnt, true)) || (rc = exchange_add(g, costs.data(), coff, ccnt, true)) ||
         (rc = exchange_end(g)))
       return rc;
   }
@@ -536,15 +558,19 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
     Member &mb = g->m[i];
     GsContext *ctx = mb.ctx;
     GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (timing) cudaEventRecord(mb.tev[GT_IMAGE], ctx->stream);
-    GS_CUDA_TRY(ctx, cudaMemcpyAsync(mb.h_row_cost[slot], mb.d_row_cost, (size_t)rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_cost[slot], ctx->stream));
+    if (timing) cudaEventRecord(mb.tev[GT_IMAGE], mb.xfer);
+    GS_CUDA_TRY(ctx, cudaMemcpyAsync(mb.h_row_cost[slot], mb.d_row_cost, (size_t)rows * 4, cudaMemcpyDeviceToHost, mb.xfer));
+    GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_cost[slot], mb.xfer));
     GsImage *rt = rts ? rts[i] : nullptr;
     if (rt && rt->memory != GS_MEM_DEVICE) {
       const uint32_t hp = rt->row_pitch_bytes ? rt->row_pitch_bytes : W * pix_bytes(fmt);
-      GS_CUDA_TRY(ctx, cudaMemcpy2DAsync(rt->data, hp, img[i], pitches[i], (size_t)W * pix_bytes(fmt), H, cudaMemcpyDeviceToHost, ctx->stream));
+      GS_CUDA_TRY(ctx, cudaMemcpy2DAsync(rt->data, hp, img[i], pitches[i], (size_t)W * pix_bytes(fmt), H, cudaMemcpyDeviceToHost, mb.xfer));
       host_out = true;
     }
+    GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_image, mb.xfer));
+    mb.image_pending = true;
+    // the row-cost vector is rewritten by the next frame's k_row_costs on the context stream: that must follow this exchange too
+    // (it does: k_row_costs runs after the compositor, which waits for ev_image)
   }
   g->frame++;
   g->hist_frames++;
@@ -559,6 +585,7 @@ int gs_group_get_stats(GsGroup *g, GsGroupStats *out) {
   GS_CUDA_TRY(mb.ctx, cudaSetDevice(mb.ctx->device));
   GS_CUDA_TRY(mb.ctx, cudaStreamSynchronize(mb.ctx->stream));
   GS_CUDA_TRY(mb.ctx, cudaStreamSynchronize(mb.aux));
+  GS_CUDA_TRY(mb.ctx, cudaStreamSynchronize(mb.xfer));
   out->group_size = g->size;
   out->rank = mb.rank;
   for (uint32_t c = 0; c <= g->size; ++c) out->row_bounds[c] = g->bounds[c];

@@ -140,6 +140,7 @@ struct SortScratch {
   uint32_t *lookback;             // passes * max_tiles * 256 status words
   uint32_t *tickets;              // passes counters
   uint32_t max_tiles;             // capacity / kSortTileItems rounded up
+  size_t lookback_words;          // size of `lookback`
 };
 constexpr uint32_t kSortTileItems = 4096;  // 256 threads x 16 keys
 size_t sort_lookback_words(uint32_t capacity, int passes);

@@ -349,8 +349,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
         // largest decoded scale in the chunk: lerp(min,max,t)^8 <= max^8 for t in [0,1]
         float sm = fmaxf(f16hi(s_chunk.sclX), fmaxf(f16hi(s_chunk.sclY), f16hi(s_chunk.sclZ)));
         sm *= sm; sm *= sm; sm *= sm;
-        const float tr = fc.extentK * sm * sm / (zmin * zmin) + 0.6f;
-        const float reach = 4.04f * fminf(sqrtf(2.0f * tr), 4096.0f) + 2.0f;
+        const float reach = quad_reach(fc.extentK * sm * sm / (zmin * zmin) + 0.3f);
         // a range partition (group path) composites only its own pixel rows: everything else on the screen is some other GPU's
         const float ylo = part.range ? (float)(part.t0 * kTile) : 0.0f, yhi = part.range ? fminf((float)(part.t1 * kTile), fc.screenH) : fc.screenH;
         cull = (x1 + reach < 0.0f) || (x0 - reach > fc.screenW) || (y1 + reach < ylo) || (y0 - reach > yhi);
@@ -488,14 +487,13 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
     auto sel_bit = [&]() -> bool { return fc.selValid && ((__ldg(selected + (idx >> 5)) >> (idx & 31)) & 1u); };
     bool far_off = false;
     if (CULL && clip.w > 0.0f) {
-      // Cheap conservative screen-extent bound BEFORE the covariance maths: lambda1 <= trace(cov2d) <= |J|_F^2 |W|_F^2 smax^2 + 0.6
-      // with |J|_F^2 <= focal^2 (2 + limX^2 + limY^2) / tz^2, and the +-2 quad reaches at most 4 * min(sqrt(2 lambda1), 4096)
+      // Cheap conservative screen-extent bound BEFORE the covariance maths: lambda1 <= |J|_2^2 |W|_2^2 smax^2 + 0.3 with
+      // |J|_2^2 = focal^2 (1 + |u|^2) / tz^2 (make_frame_consts, gs_api.cu), and the +-2 quad reaches at most quad_reach()
       // pixels from its centre.  A splat whose centre is further than that outside the screen can never produce a fragment:
       // the fused frame stores {pos, 0, 0} for it and skips rotation, covariance, eigen-decomposition and colour.
       const float tzq = fmaf(fc.mv[10], pos.z, fmaf(fc.mv[9], pos.y, fmaf(fc.mv[8], pos.x, fc.mv[11])));
       const float smax = fmaxf(scale.x, fmaxf(scale.y, scale.z));
-      const float tr = fc.extentK * smax * smax / (tzq * tzq) + 0.6f;
-      const float reach = 4.04f * fminf(sqrtf(2.0f * tr), 4096.0f) + 2.0f;
+      const float reach = quad_reach(fc.extentK * smax * smax / (tzq * tzq) + 0.3f);
       const float iw = 1.0f / clip.w;
       const float pcx = (clip.x * iw * 0.5f + 0.5f) * fc.screenW, pcy = (0.5f - 0.5f * clip.y * iw) * fc.screenH;
       const float ylo = part.range ? (float)(part.t0 * kTile) : 0.0f, yhi = part.range ? fminf((float)(part.t1 * kTile), fc.screenH) : fc.screenH;
