@@ -46,6 +46,8 @@ struct Member {
   cudaEvent_t ev_produced = nullptr, ev_consumed = nullptr;   // emulated exchange
   cudaEvent_t tev[GT_COUNT]{};
   uint32_t *d_info = nullptr, *d_slab_count = nullptr, *d_cmp_status = nullptr, *d_row_cost = nullptr;
+  uint32_t *d_gather = nullptr;   // staging of the order exchange: G slabs of `cap` ids each (the all-gather's buffer)
+  size_t gather_words = 0;
   size_t cmp_words = 0;
   uint32_t rows_cap = 0;
   uint32_t *h_info = nullptr, *h_row_cost[2] = {nullptr, nullptr};   // pinned
@@ -106,7 +108,7 @@ void member_free(Member &mb) {
   cudaEvent_t evs[] = {mb.ev_begin, mb.ev_view, mb.ev_info, mb.ev_cost[0], mb.ev_cost[1], mb.ev_produced, mb.ev_consumed, mb.ev_raster, mb.ev_image};
   for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
   for (int i = 0; i < GT_COUNT; ++i) if (mb.tev[i]) cudaEventDestroy(mb.tev[i]);
-  cudaFree(mb.d_info); cudaFree(mb.d_slab_count); cudaFree(mb.d_cmp_status); cudaFree(mb.d_row_cost); cudaFree(mb.rt_scratch);
+  cudaFree(mb.d_info); cudaFree(mb.d_slab_count); cudaFree(mb.d_cmp_status); cudaFree(mb.d_row_cost); cudaFree(mb.rt_scratch); cudaFree(mb.d_gather);
   cudaFreeHost(mb.h_info); cudaFreeHost(mb.h_row_cost[0]); cudaFreeHost(mb.h_row_cost[1]);
   if (mb.comm && nccl_api().ok()) nccl_api().CommDestroy(mb.comm);
   if (mb.own_ctx) gs_destroy(mb.ctx);
@@ -192,6 +194,39 @@ int exchange_add(GsGroup *g, uint8_t *const *bufs, const size_t *off, const size
 int exchange_end(GsGroup *g) {
   if (g->use_nccl) GS_NCCL_TRY(g->m[0].ctx, nccl_api().GroupEnd());
   return GS_OK;
+}
+
+// The order exchange as ONE ncclAllGather: NCCL's all-gather moves the 24.5 MB of cfg2 in 60 us on two B200s where grouped
+// broadcasts / send-recv of the exact slab sizes take 97 (tools/mb_exchange.py), so every GPU sorts its slab into slot `rank`
+// of a staging buffer of G equal slots (cap = the largest slab), the slots are gathered in place, and k_unpack_slabs copies
+// slot c's first cnt[c] ids to their place off[c] of the order (one coalesced read + write of the order).
+struct SlabLayout { uint32_t off[GS_GROUP_MAX_GPUS + 1]; uint32_t count, cap; };
+
+__global__ void __launch_bounds__(256) k_unpack_slabs(const uint32_t *__restrict__ staging, SlabLayout lay, uint32_t *__restrict__ order) {
+  const uint32_t n = lay.off[lay.count];
+  for (uint32_t p = blockIdx.x * 256 + threadIdx.x; p < n; p += gridDim.x * 256) {
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t k = 1; k < GS_GROUP_MAX_GPUS; ++k) c += (k < lay.count && p >= lay.off[k]) ? 1u : 0u;
+    order[p] = __ldg(staging + (size_t)c * lay.cap + (p - lay.off[c]));
+  }
+}
+
+int exchange_allgather(GsGroup *g, uint8_t *const *bufs, size_t slot_bytes, const size_t *cnt) {
+  const uint32_t G = g->size;
+  if (g->use_nccl) {
+    const NcclApi &nc = nccl_api();
+    GS_NCCL_TRY(g->m[0].ctx, nc.GroupStart());
+    for (size_t i = 0; i < g->m.size(); ++i) {
+      Member &mb = g->m[i];
+      GS_NCCL_TRY(mb.ctx, nc.AllGather(bufs[i] + (size_t)mb.rank * slot_bytes, bufs[i], slot_bytes, ncclUint8, mb.comm, mb.ctx->stream));
+    }
+    GS_NCCL_TRY(g->m[0].ctx, nc.GroupEnd());
+    return GS_OK;
+  }
+  size_t off[GS_GROUP_MAX_GPUS];
+  for (uint32_t c = 0; c < G; ++c) off[c] = (size_t)c * slot_bytes;
+  return exchange_add(g, bufs, off, cnt);   // device copies of the filled part of every slot
 }
 
 void balance_rows(const uint32_t *cost, uint32_t rows, uint32_t parts, uint32_t *bounds) {
@@ -456,6 +491,29 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
 
     // ---- phase C: compact my slab out of last frame's order, sort it into its place of the new order ------------------
     GsNvtxRange nvtx_sort("GaussianSplat.Sort");
+    // equal slots + one all-gather while the slabs are reasonably balanced (they are after the first frame); a frame whose
+    // largest slab is far above N/G exchanges the exact sizes in place instead (no G x cap staging)
+    uint32_t cap = 0;
+    for (uint32_t c = 0; c < G; ++c) cap = g->slab_cnt[c] > cap ? g->slab_cnt[c] : cap;
+    cap = (cap + 3u) & ~3u;
+    static int ag_env = -1;
+    if (ag_env < 0) { const char *e = getenv("GS_GROUP_ORDER_ALLGATHER"); ag_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool use_gather = G > 1 && ag_env && g->xfer == 0 && (uint64_t)cap * G <= (uint64_t)N + (uint64_t)N / 2 + 64u * G;
+    if (use_gather) {
+      for (size_t i = 0; i < L; ++i) {
+        Member &mb = g->m[i];
+        const size_t need = (size_t)cap * G;
+        if (need > mb.gather_words) {
+          GS_CUDA_TRY(mb.ctx, cudaSetDevice(mb.ctx->device));
+          cudaStreamSynchronize(mb.ctx->stream);
+          cudaFree(mb.d_gather);
+          mb.d_gather = nullptr; mb.gather_words = 0;
+          const size_t words = (size_t)N + (size_t)N / 2 + 64u * G;   // the largest staging this path ever uses
+          GS_CUDA_TRY(mb.ctx, cudaMalloc(&mb.d_gather, words * 4));
+          mb.gather_words = words;
+        }
+      }
+    }
     for (size_t i = 0; i < L; ++i) {
       Member &mb = g->m[i];
       GsContext *ctx = mb.ctx;
@@ -469,7 +527,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
         launch_compact_order(as->order, N, as->slab_mask, as->slab_group_flag, as->key_table, as->order_tmp, as->keys, mb.d_cmp_status, mb.d_slab_count,
                              ctx->stream);
         launch_sort_pairs(as->keys, as->order_tmp, mb.d_slab_count, cnt, 4, 8, true, ctx->sort, ctx->stream, nullptr, nullptr, true,
-                          as->keys + off, as->order + off);
+                          as->keys + off, use_gather ? mb.d_gather + (size_t)mb.rank * cap : as->order + off);
         ctx->launches += 5;
       }
       GS_CUDA_TRY(ctx, cudaGetLastError());
@@ -479,8 +537,24 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
       std::vector<uint8_t *> bufs(L);
       size_t off[GS_GROUP_MAX_GPUS], cnt[GS_GROUP_MAX_GPUS];
       for (uint32_t c = 0; c < G; ++c) { off[c] = (size_t)g->slab_off[c] * 4; cnt[c] = (size_t)g->slab_cnt[c] * 4; }
-      for (size_t i = 0; i < L; ++i) bufs[i] = reinterpret_cast<uint8_t *>(assets[i]->order);
-      if ((rc = exchange_begin(g)) || (rc = exchange_add(g, bufs.data(), off, cnt)) || (rc = exchange_end(g))) return rc;
+      if (use_gather) {
+        for (size_t i = 0; i < L; ++i) bufs[i] = reinterpret_cast<uint8_t *>(g->m[i].d_gather);
+        if ((rc = exchange_allgather(g, bufs.data(), (size_t)cap * 4, cnt))) return rc;
+        SlabLayout lay;
+        memset(&lay, 0, sizeof(lay));
+        for (uint32_t c = 0; c <= G; ++c) lay.off[c] = g->slab_off[c];
+        lay.count = G; lay.cap = cap;
+        for (size_t i = 0; i < L; ++i) {
+          Member &mb = g->m[i];
+          GS_CUDA_TRY(mb.ctx, cudaSetDevice(mb.ctx->device));
+          k_unpack_slabs<<<148 * 8, 256, 0, mb.ctx->stream>>>(mb.d_gather, lay, assets[i]->order);
+          mb.ctx->launches += 1;
+          GS_CUDA_TRY(mb.ctx, cudaGetLastError());
+        }
+      } else {
+        for (size_t i = 0; i < L; ++i) bufs[i] = reinterpret_cast<uint8_t *>(assets[i]->order);
+        if ((rc = exchange_begin(g)) || (rc = exchange_add(g, bufs.data(), off, cnt)) || (rc = exchange_end(g))) return rc;
+      }
     }
   }
   if (timing) for (Member &mb : g->m) { cudaSetDevice(mb.ctx->device); if (!do_sort_flag) cudaEventRecord(mb.tev[GT_SORT], mb.ctx->stream); cudaEventRecord(mb.tev[GT_ORDER], mb.ctx->stream); }

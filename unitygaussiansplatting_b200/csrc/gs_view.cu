@@ -535,6 +535,20 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
       float cov01 = T[0][0] * vt[0][1] + T[0][1] * vt[1][1] + T[0][2] * vt[2][1];
       float cov11 = T[1][0] * vt[0][1] + T[1][1] * vt[1][1] + T[1][2] * vt[2][1];
       cov00 += 0.3f; cov11 += 0.3f;
+      // Second-stage cull (fused frame only), now that the 2-D covariance is known: the quad's half extents are
+      // 2 (l1 |v_x| + l2 |v_y|) with l_i^2 = 2 lambda_i (lambda2 raised to 0.1 at most), and by Cauchy-Schwarz
+      // l1 |v_x| + l2 |v_y| <= sqrt(2) sqrt(l1^2 v_x^2 + l2^2 v_y^2) <= sqrt(2) sqrt(2 cov00 + 0.2): at most 4 sqrt(cov + 0.1)
+      // pixels per axis, a factor sqrt(2) from exact.  A quad that cannot reach the screen -- or, in a group, this GPU's rows --
+      // skips eigen-decomposition, footprint and colour.
+      bool reachable = true;
+      if (CULL) {
+        const float rx = 4.04f * sqrtf(cov00 + 0.1f) + 2.0f, ry = 4.04f * sqrtf(cov11 + 0.1f) + 2.0f;
+        const float iw = 1.0f / clip.w;
+        const float pcx = (clip.x * iw * 0.5f + 0.5f) * fc.screenW, pcy = (0.5f - 0.5f * clip.y * iw) * fc.screenH;
+        const float ylo = part.range ? (float)(part.t0 * kTile) : 0.0f, yhi = part.range ? fminf((float)(part.t1 * kTile), fc.screenH) : fc.screenH;
+        reachable = !((pcx + rx < 0.0f) || (pcx - rx > fc.screenW) || (pcy + ry < ylo) || (pcy - ry > yhi));
+      }
+      if (reachable) {
       // DecomposeCovariance, S/SplatUtilities.compute:149-159
       float mid = 0.5f * (cov00 + cov11);
       float hd = (cov00 - cov11) * 0.5f;
@@ -607,6 +621,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
           d[2] = make_float4(f16hi(vw[8]), f16lo(vw[8]), f16hi(vw[9]), fp.hy);
         }
       }
+      }  // reachable
     }
     rect_out[idx] = rect;
   }
@@ -647,6 +662,8 @@ void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *
   const float4 row = make_float4(fc.sort_row[0], fc.sort_row[1], fc.sort_row[2], fc.sort_row[3]);
   SlabArgs none{};
   if (!slabs || slabs->count <= 1) k_calc_distances<0><<<grid, 256, 0, s>>>(a, row, key_table, ghist, none);
+  else if (slabs->count <= 2) k_calc_distances<1><<<grid, 256, 0, s>>>(a, row, key_table, ghist, *slabs);
+  else if (slabs->count <= 4) k_calc_distances<3><<<grid, 256, 0, s>>>(a, row, key_table, ghist, *slabs);
   else if (slabs->count <= 8) k_calc_distances<7><<<grid, 256, 0, s>>>(a, row, key_table, ghist, *slabs);
   else k_calc_distances<kMaxSlabs - 1><<<grid, 256, 0, s>>>(a, row, key_table, ghist, *slabs);
 }
