@@ -260,7 +260,7 @@ int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameCon
   if (rc) return rc;
   const bool own = stream == ctx->stream;   // the group path runs view-calc beside the sort on a second stream and times it itself
   if (own) rec(ctx, EV_VIEW0);
-  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, ctx->d_selected, as->view, as->rect, as->draw, as->block_flag, cull, make_partition(opt), stream);
+  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, ctx->d_selected, as->view, as->rect, as->draw, as->block_bits, cull, make_partition(opt), stream);
   if (own) rec(ctx, EV_VIEW1);
   ctx->launches += 1;
   as->view_valid = !cull;
@@ -300,7 +300,7 @@ int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const GsRender
     }
   }
   int bin_launches = 0;
-  const BinScratch lists = launch_binning(fc, opt, as->av.n, as->order, as->rect, as->block_flag, ctx->bin, ctx->sort, ctx->stream, &bin_launches);
+  const BinScratch lists = launch_binning(fc, opt, as->av.n, as->order, as->rect, as->block_bits, ctx->bin, ctx->sort, ctx->stream, &bin_launches);
   rec(ctx, EV_BIN1);
   launch_raster(fc, opt, as->draw, lists, d_rt, pitch, fmt, ctx->stream);
   rec(ctx, EV_RASTER1);
@@ -510,7 +510,7 @@ int gs_asset_upload(GsContext *ctx, const GsAssetDesc *d, GsAsset **out) {
       (e = cudaMalloc(&as->order, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->keys, n * 4)) != cudaSuccess ||
       (e = cudaMalloc(&as->key_table, n * 4)) != cudaSuccess || (e = cudaMalloc(&as->draw, n * 48)) != cudaSuccess ||
       (e = cudaMalloc(&as->view, n * kViewStride + 16)) != cudaSuccess || (e = cudaMalloc(&as->rect, n * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&as->d_n, 4)) != cudaSuccess || (e = cudaMalloc(&as->block_flag, (n + 255) / 256 + 64)) != cudaSuccess) {
+      (e = cudaMalloc(&as->d_n, 4)) != cudaSuccess || (e = cudaMalloc(&as->block_bits, block_bits_words(d->splat_count) * 4 + 64)) != cudaSuccess) {
     gs_asset_destroy(as);
     return fail_cuda(ctx, e, "asset upload", __FILE__, __LINE__);
   }
@@ -532,7 +532,7 @@ void gs_asset_destroy(GsAsset *as) {
   if (!as) return;
   if (as->ctx) { cudaSetDevice(as->ctx->device); cudaStreamSynchronize(as->ctx->stream); }
   cudaFree(as->d_pos); cudaFree(as->d_other); cudaFree(as->d_sh); cudaFree(as->d_color); cudaFree(as->d_chunks);
-  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->draw); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n); cudaFree(as->block_flag); cudaFree(as->slab_mask); cudaFree(as->order_tmp); cudaFree(as->slab_group_flag);
+  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->draw); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n); cudaFree(as->block_bits); cudaFree(as->slab_mask); cudaFree(as->order_tmp); cudaFree(as->slab_group_bits);
   delete as;
 }
 

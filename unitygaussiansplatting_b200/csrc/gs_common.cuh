@@ -71,6 +71,37 @@ __host__ __device__ __forceinline__ uint32_t vec_stride(uint32_t fmt) {
 // absorb float rounding and the slight non-orthonormality of an un-renormalised decoded rotation.
 __device__ __forceinline__ float quad_reach(float l1sq) { return 2.9f * fminf(sqrtf(2.0f * l1sq), 4096.0f) + 2.0f; }
 
+// ---- decoupled look-back over single-word block statuses, 32 predecessors per round ----------------------------------
+// status[b] = (LOCAL | total) once block b knows its own total, (INCL | inclusive prefix) once it knows everything before
+// it too; 0 = not published yet.  Called by ONE WARP of block b (b > 0), returns the exclusive prefix of b to every lane.
+// (A 128-wide variant -- four predecessors per lane -- was measured on B200 and is SLOWER: 114 vs 68 us for the binner of one
+// GPU of four on cfg2.  A round can only be summed once ALL the polled predecessors have published, so a wider round waits
+// for the slowest of four times as many blocks; the wait for neighbours to publish, not the number of rounds, is what
+// the barrier stalls in ncu are.)  Sums saturate at the value mask (callers treat a saturated total as overflow).
+enum : uint32_t { kLbLocal = 1u << 30, kLbIncl = 2u << 30, kLbMask = (1u << 30) - 1u };
+
+__device__ __forceinline__ uint32_t lookback_exclusive(volatile uint32_t *status, uint32_t b) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t excl = 0;
+  int top = (int)b - 1;
+  while (true) {
+    const int idx = top - (int)lane;
+    uint32_t v;
+    do {
+      v = idx >= 0 ? status[idx] : (uint32_t)kLbIncl;
+    } while (__any_sync(0xffffffffu, v == 0));
+    const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v & kLbIncl) != 0);
+    const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;   // nearest predecessor that is already inclusive
+    uint32_t contrib = ((int)lane <= first) ? (v & (uint32_t)kLbMask) : 0u;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) contrib = min(contrib + __shfl_xor_sync(0xffffffffu, contrib, o), (uint32_t)kLbMask);
+    excl = min(excl + contrib, (uint32_t)kLbMask);
+    if (incl_mask) break;
+    top -= 32;
+  }
+  return excl;
+}
+
 // ---- small device helpers -------------------------------------------------------------
 __device__ __forceinline__ float f16lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
 __device__ __forceinline__ float f16hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }

@@ -133,7 +133,7 @@ int member_asset(Member &mb, GsAsset *as) {   // per-asset buffers only the grou
   const uint32_t n = as->av.n;
   if (!as->slab_mask) GS_CUDA_TRY(ctx, cudaMalloc(&as->slab_mask, ((size_t)(n + 1023) / 1024) * 128 + 64));
   if (!as->order_tmp) GS_CUDA_TRY(ctx, cudaMalloc(&as->order_tmp, (size_t)n * 4 + 16));
-  if (!as->slab_group_flag) GS_CUDA_TRY(ctx, cudaMalloc(&as->slab_group_flag, (size_t)(n + 127) / 128 + 64));
+  if (!as->slab_group_bits) GS_CUDA_TRY(ctx, cudaMalloc(&as->slab_group_bits, group_bits_words(n) * 4 + 64));
   const size_t words = compact_status_words(n);
   if (words > mb.cmp_words) {
     cudaStreamSynchronize(ctx->stream);
@@ -198,19 +198,9 @@ int exchange_end(GsGroup *g) {
 
 // The order exchange as ONE ncclAllGather: NCCL's all-gather moves the 24.5 MB of cfg2 in 60 us on two B200s where grouped
 // broadcasts / send-recv of the exact slab sizes take 97 (tools/mb_exchange.py), so every GPU sorts its slab into slot `rank`
-// of a staging buffer of G equal slots (cap = the largest slab), the slots are gathered in place, and k_unpack_slabs copies
-// slot c's first cnt[c] ids to their place off[c] of the order (one coalesced read + write of the order).
+// of a staging buffer of G equal slots (cap = the largest slab), the slots are gathered in place, and G device copies move
+// slot c's first cnt[c] ids to their place off[c] of the order.
 struct SlabLayout { uint32_t off[GS_GROUP_MAX_GPUS + 1]; uint32_t count, cap; };
-
-__global__ void __launch_bounds__(256) k_unpack_slabs(const uint32_t *__restrict__ staging, SlabLayout lay, uint32_t *__restrict__ order) {
-  const uint32_t n = lay.off[lay.count];
-  for (uint32_t p = blockIdx.x * 256 + threadIdx.x; p < n; p += gridDim.x * 256) {
-    uint32_t c = 0;
-#pragma unroll
-    for (uint32_t k = 1; k < GS_GROUP_MAX_GPUS; ++k) c += (k < lay.count && p >= lay.off[k]) ? 1u : 0u;
-    order[p] = __ldg(staging + (size_t)c * lay.cap + (p - lay.off[c]));
-  }
-}
 
 int exchange_allgather(GsGroup *g, uint8_t *const *bufs, size_t slot_bytes, const size_t *cnt) {
   const uint32_t G = g->size;
@@ -429,6 +419,28 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
 
   const bool timing = g->m[0].ctx->timing;
   g->timed = timing;
+  // View-calc reads nothing the sort writes: it runs on the helper stream (lowest priority).  By default it starts with the
+  // frame and fills whatever the sort chain leaves idle (the host wait for the slab table, kernel tails, the exchange);
+  // GS_GROUP_VIEW_LATE=1 starts it only when the slab sort is done, i.e. squarely under the order exchange.
+  static int view_late_env = -1;
+  if (view_late_env < 0) { const char *e = getenv("GS_GROUP_VIEW_LATE"); view_late_env = (e && e[0] == '1') ? 1 : 0; }
+  const bool view_late = view_late_env && do_sort_flag && G > 1;
+  auto enqueue_view = [&](size_t i, cudaEvent_t after) -> int {
+    Member &mb = g->m[i];
+    GsContext *ctx = mb.ctx;
+    GsRenderOptions opt = base;
+    opt.row_begin = g->bounds[mb.rank]; opt.row_end = g->bounds[mb.rank + 1];
+    if (opt.row_end > opt.row_begin || G == 1) {
+      if (G == 1) opt.row_begin = opt.row_end = 0;
+      GS_CUDA_TRY(ctx, cudaStreamWaitEvent(mb.aux, after, 0));
+      if (timing) cudaEventRecord(mb.tev[GT_V0], mb.aux);
+      int r = do_view(ctx, assets[i], fp, fc, true, opt, mb.aux);
+      if (r) return r;
+      if (timing) cudaEventRecord(mb.tev[GT_V1], mb.aux);
+      GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_view, mb.aux));
+    }
+    return GS_OK;
+  };
   GsNvtxRange nvtx_frame("GaussianSplat.GroupFrame");
   // ---- phase A: distances + slab table on the context stream; view-calc on the second stream --------------------------
   for (size_t i = 0; i < L; ++i) {
@@ -443,7 +455,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
     if (do_sort_flag) {
       SlabArgs sl;
       memset(&sl, 0, sizeof(sl));
-      sl.count = G; sl.index = mb.rank; sl.order_prev = as->order; sl.mask = as->slab_mask; sl.group_flag = as->slab_group_flag; sl.info = mb.d_info;
+      sl.count = G; sl.index = mb.rank; sl.order_prev = as->order; sl.mask = as->slab_mask; sl.group_bits = as->slab_group_bits; sl.info = mb.d_info;
       for (uint32_t j = 0; j + 1 < G; ++j) sl.qpos[j] = (uint32_t)(((uint64_t)N * (j + 1)) / G);
       GS_CUDA_TRY(ctx, cudaMemsetAsync(ctx->sort.ghist, 0, 4 * 256 * 4, ctx->stream));
       GS_CUDA_TRY(ctx, cudaMemsetAsync(mb.d_info, 0, 2 * kMaxSlabs * 4, ctx->stream));
@@ -455,17 +467,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
       }
     }
     if (timing) cudaEventRecord(mb.tev[GT_DIST], ctx->stream);
-    // view-calc reads nothing the sort writes; it must only wait for whatever used rect / draw records before this frame
-    GsRenderOptions opt = base;
-    opt.row_begin = g->bounds[mb.rank]; opt.row_end = g->bounds[mb.rank + 1];
-    if (opt.row_end > opt.row_begin || G == 1) {
-      if (G == 1) opt.row_begin = opt.row_end = 0;
-      GS_CUDA_TRY(ctx, cudaStreamWaitEvent(mb.aux, mb.ev_begin, 0));
-      if (timing) cudaEventRecord(mb.tev[GT_V0], mb.aux);
-      if ((rc = do_view(ctx, as, fp, fc, true, opt, mb.aux))) return rc;
-      if (timing) cudaEventRecord(mb.tev[GT_V1], mb.aux);
-      GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_view, mb.aux));
-    }
+    if (!view_late && (rc = enqueue_view(i, mb.ev_begin))) return rc;
   }
 
   // ---- slab sizes: the one host wait of the frame (the GPUs are busy with view-calc) ----------------------------------
@@ -524,7 +526,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
         launch_sort_pairs(as->keys, as->order, as->d_n, N, 4, 8, true, ctx->sort, ctx->stream, nullptr, as->key_table);
         ctx->launches += 4;
       } else if (cnt) {
-        launch_compact_order(as->order, N, as->slab_mask, as->slab_group_flag, as->key_table, as->order_tmp, as->keys, mb.d_cmp_status, mb.d_slab_count,
+        launch_compact_order(as->order, N, as->slab_mask, as->slab_group_bits, as->key_table, as->order_tmp, as->keys, mb.d_cmp_status, mb.d_slab_count,
                              ctx->stream);
         launch_sort_pairs(as->keys, as->order_tmp, mb.d_slab_count, cnt, 4, 8, true, ctx->sort, ctx->stream, nullptr, nullptr, true,
                           as->keys + off, use_gather ? mb.d_gather + (size_t)mb.rank * cap : as->order + off);
@@ -532,6 +534,10 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
       }
       GS_CUDA_TRY(ctx, cudaGetLastError());
       if (timing) cudaEventRecord(mb.tev[GT_SORT], ctx->stream);
+      if (view_late) {
+        GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_produced, ctx->stream));   // (free until the exchange records it again)
+        if ((rc = enqueue_view(i, mb.ev_produced))) return rc;
+      }
     }
     if (G > 1) {
       std::vector<uint8_t *> bufs(L);
@@ -544,12 +550,14 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
         memset(&lay, 0, sizeof(lay));
         for (uint32_t c = 0; c <= G; ++c) lay.off[c] = g->slab_off[c];
         lay.count = G; lay.cap = cap;
-        for (size_t i = 0; i < L; ++i) {
-          Member &mb = g->m[i];
+        (void)lay;
+        for (size_t i = 0; i < L; ++i) {   // slot c's ids -> their place in the order: G device copies (a copy kernel that found
+          Member &mb = g->m[i];            // each element's slab took 41 us for the 24.5 MB of cfg2; the copy engine takes ~10)
           GS_CUDA_TRY(mb.ctx, cudaSetDevice(mb.ctx->device));
-          k_unpack_slabs<<<148 * 8, 256, 0, mb.ctx->stream>>>(mb.d_gather, lay, assets[i]->order);
-          mb.ctx->launches += 1;
-          GS_CUDA_TRY(mb.ctx, cudaGetLastError());
+          for (uint32_t c = 0; c < G; ++c)
+            if (g->slab_cnt[c])
+              GS_CUDA_TRY(mb.ctx, cudaMemcpyAsync(assets[i]->order + g->slab_off[c], mb.d_gather + (size_t)c * cap, (size_t)g->slab_cnt[c] * 4,
+                                                  cudaMemcpyDeviceToDevice, mb.ctx->stream));
         }
       } else {
         for (size_t i = 0; i < L; ++i) bufs[i] = reinterpret_cast<uint8_t *>(assets[i]->order);

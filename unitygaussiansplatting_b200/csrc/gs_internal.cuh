@@ -69,10 +69,10 @@ struct GsAsset {
   gs::AssetView av{};
   void *d_pos = nullptr, *d_other = nullptr, *d_sh = nullptr, *d_color = nullptr, *d_chunks = nullptr;
   uint32_t *order = nullptr, *keys = nullptr, *key_table = nullptr, *view = nullptr, *rect = nullptr, *d_n = nullptr;
-  uint8_t *block_flag = nullptr;   // byte j: some splat of block j (256 splats) got a bin rectangle from the last view-calc
+  uint32_t *block_bits = nullptr;  // bit j: some splat of block j (256 splats) got a bin rectangle from the last view-calc
   // group path only (allocated by gs_group_*): slab membership (bit per splat, byte per 128), compaction output / sort ping-pong payload
   uint32_t *slab_mask = nullptr, *order_tmp = nullptr;
-  uint8_t *slab_group_flag = nullptr;
+  uint32_t *slab_group_bits = nullptr;
   float4 *draw = nullptr;  // raster-ready 48-byte records of the drawable splats
   bool view_valid = false;   // the full 40-byte _SplatViewData buffer is current (gs_calc_view)
   bool draw_valid = false;   // draw records + bin rects are current (gs_calc_view or gs_frame)

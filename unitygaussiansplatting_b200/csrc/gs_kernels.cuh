@@ -124,14 +124,16 @@ struct SlabArgs {
   const uint32_t *order_prev;     // last frame's draw order (replicated)
   uint32_t qpos[kMaxSlabs - 1];   // positions in order_prev whose splats' current keys are the G-1 splitters
   uint32_t *mask;                 // out: bit i = splat i belongs to slab `index`
-  uint8_t *group_flag;            // out: byte j = some splat of [128 j, 128 j + 128) belongs to slab `index`
+  uint32_t *group_bits;           // out: bit j = some splat of [128 j, 128 j + 128) belongs to slab `index` (group_bits_words(n) words)
   uint32_t *info;                 // out (zeroed by the caller): [0, kMaxSlabs) ascending splitters, [kMaxSlabs, 2 kMaxSlabs) #{key >= splitter j}
 };
 void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *key_table, uint32_t *ghist, cudaStream_t s,
                            const SlabArgs *slabs = nullptr);
-// block_flag: ceil(n / 256) bytes, byte j = some splat of [256 j, 256 j + 256) got a bin rectangle
+// block_bits: block_bits_words(n) words, bit j = some splat of [256 j, 256 j + 256) got a bin rectangle
+inline size_t block_bits_words(uint32_t n) { return ((size_t)(n + 255) / 256 + 31) / 32 + 1; }
+inline size_t group_bits_words(uint32_t n) { return ((size_t)(n + 127) / 128 + 31) / 32 + 1; }
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
-                      uint32_t *rect, float4 *draw, uint8_t *block_flag, bool cull_undrawable, const Partition &part, cudaStream_t s);
+                      uint32_t *rect, float4 *draw, uint32_t *block_bits, bool cull_undrawable, const Partition &part, cudaStream_t s);
 
 // Radix sort (gs_sort.cu).  Scratch layout is owned by the caller (gs_api.cu).
 struct SortScratch {
@@ -154,10 +156,10 @@ void launch_sort_pairs(uint32_t *keys, uint32_t *vals, const uint32_t *d_count, 
                        const SortScratch &sc, cudaStream_t s, cudaEvent_t *pass_events = nullptr, const uint32_t *key_table = nullptr,
                        bool count_is_capacity = true, uint32_t *final_keys = nullptr, uint32_t *final_vals = nullptr);
 // (out_ids, out_keys) = (id, key_table[id]) of the ids of order[0..n) whose mask bit is set, order kept; *count_out = how many.
-// group_flag (bytes, one per 128 ids) lets whole groups be skipped without reading their mask words.
+// group_bits (one bit per 128 ids, kept in shared memory) lets whole groups be skipped without reading their mask words.
 // status: compact_status_words(n) words of scratch.
 size_t compact_status_words(uint32_t n);
-void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mask, const uint8_t *group_flag, const uint32_t *key_table,
+void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mask, const uint32_t *group_bits, const uint32_t *key_table,
                           uint32_t *out_ids, uint32_t *out_keys, uint32_t *status, uint32_t *count_out, cudaStream_t s);
 
 // Binning + raster + composite (gs_raster.cu)
@@ -171,7 +173,7 @@ struct BinScratch {
 };
 // returns the scratch view whose tile_keys / tile_vals hold the bin-sorted lists (launch_raster's input)
 BinScratch launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
-                          const uint8_t *block_flag, const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *launches);
+                          const uint32_t *block_bits, const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *launches);
 void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
                    uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s);
 extern unsigned long long *g_raster_stats;   // diagnostics, see GS_RASTER_STATS

@@ -30,12 +30,12 @@ constexpr int kBinBlock = 256 * kBinItems;    // ranks per block
 
 // ---- 1. count + scan + emit in ONE pass ---------------------------------------------------------
 // Blocks take their index by atomic ticket, publish their entry total with a LOCAL flag, resolve
-// their exclusive offset by a warp-parallel decoupled look-back (32 predecessors per probe), then
+// their exclusive offset by a warp-parallel decoupled look-back (32 predecessors per probe, gs_common.cuh), then
 // emit (tile id, splat id) entries in depth order.  Emission is warp-cooperative: the 32 ranks a warp
 // holds for one item slot own one contiguous output range; lane x of the warp writes entry x of that
 // range (owner found by a 5-step shuffle search over the lanes' prefix sums), so every store is a
 // full coalesced line regardless of how many tiles each splat touches.
-enum : uint32_t { kBinFlagLocal = 1u << 30, kBinFlagIncl = 2u << 30, kBinValMask = (1u << 30) - 1u };
+enum : uint32_t { kBinFlagLocal = kLbLocal, kBinFlagIncl = kLbIncl, kBinValMask = kLbMask };
 
 __device__ __forceinline__ uint32_t entry_tile(uint32_t e, uint32_t r, const Partition &p, uint32_t tilesX) {
   const uint32_t x0 = r & 255u, y0 = (r >> 8) & 255u, x1 = (r >> 16) & 255u;
@@ -47,16 +47,19 @@ __device__ __forceinline__ uint32_t entry_tile(uint32_t e, uint32_t r, const Par
 }
 
 __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ order, const uint32_t *__restrict__ rect,
-                                                  const uint8_t *__restrict__ block_flag, uint32_t n, Partition part, uint32_t tilesX, volatile uint32_t *status,
+                                                  const uint32_t *__restrict__ block_bits, uint32_t bits_words, uint32_t n, Partition part,
+                                                  uint32_t tilesX, volatile uint32_t *status,
                                                   uint32_t *ticket, uint32_t capacity, uint32_t *__restrict__ keys,
                                                   uint32_t *__restrict__ vals, uint32_t *__restrict__ entry_count,
                                                   uint32_t *__restrict__ ghist, uint32_t digit_bits, bool two_pass) {
+  extern __shared__ uint32_t s_bits[];   // the view kernel's block bitmap (bits_words words), or nothing when it is too large to hold
   __shared__ uint32_t s_w[8];
   __shared__ uint32_t s_block, s_excl;
   __shared__ uint32_t s_dh[512];   // digit histograms of the two sort passes over the tile ids we emit
   const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
+  for (uint32_t i = threadIdx.x; i < bits_words; i += 256) s_bits[i] = __ldg(block_bits + i);
   s_dh[threadIdx.x] = 0; s_dh[threadIdx.x + 256] = 0;
   const uint32_t dmask = (1u << digit_bits) - 1u;
   __syncthreads();
@@ -71,9 +74,16 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
     id[i] = (r < n) ? __ldg(order + r) : 0xFFFFFFFFu;
   }
 #pragma unroll
-  // the rectangle of a splat is a random 4-byte gather; the view kernel's per-block flags (n/256 bytes: L1-resident) say
-  // where there is nothing to fetch
-  for (int i = 0; i < kBinItems; ++i) rc[i] = (id[i] != 0xFFFFFFFFu && __ldg(block_flag + (id[i] >> 8))) ? __ldg(rect + id[i]) : kRectEmpty;
+  // the rectangle of a splat is a random 4-byte gather; the view kernel's per-block bits (in shared memory) say where there
+  // is nothing to fetch
+#pragma unroll
+  for (int i = 0; i < kBinItems; ++i) {
+    rc[i] = kRectEmpty;
+    if (id[i] != 0xFFFFFFFFu) {
+      const uint32_t bw = bits_words ? s_bits[id[i] >> 13] : __ldg(block_bits + (id[i] >> 13));
+      if ((bw >> ((id[i] >> 8) & 31u)) & 1u) rc[i] = __ldg(rect + id[i]);
+    }
+  }
   uint32_t wtot[kBinItems], wsum = 0;
 #pragma unroll
   for (int i = 0; i < kBinItems; ++i) {
@@ -101,22 +111,7 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
     if (lane == 0) status[b] = (b == 0 ? kBinFlagIncl : kBinFlagLocal) | total;
     uint32_t excl = 0;
     if (b > 0) {
-      int top = (int)b - 1;
-      while (true) {
-        const int idx = top - (int)lane;
-        uint32_t v;
-        do {
-          v = idx >= 0 ? status[idx] : (uint32_t)kBinFlagIncl;
-        } while (__any_sync(0xffffffffu, v == 0));
-        const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v & kBinFlagIncl) != 0);
-        const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;   // nearest predecessor that is already inclusive
-        uint32_t contrib = ((int)lane <= first) ? (v & kBinValMask) : 0u;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) contrib = min(contrib + __shfl_xor_sync(0xffffffffu, contrib, o), (uint32_t)kBinValMask);
-        excl = min(excl + contrib, (uint32_t)kBinValMask);
-        if (incl_mask) break;
-        top -= 32;
-      }
+      excl = lookback_exclusive(status, b);
       // prefixes saturate instead of wrapping at 2^30: a saturated total is > any capacity, so it is reported as overflow
       if (lane == 0) status[b] = kBinFlagIncl | min(excl + total, (uint32_t)kBinValMask);
     }
@@ -175,7 +170,7 @@ static void bin_sort_plan(uint32_t bins, int *bits, int *passes) {
 }
 
 BinScratch launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uint32_t n, const uint32_t *order, const uint32_t *rect,
-                          const uint8_t *block_flag, const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *launches) {
+                          const uint32_t *block_bits, const BinScratch &bs, const SortScratch &sc, cudaStream_t s, int *launches) {
   const Partition part = make_partition(opt);
   const uint32_t tiles = fc.binsX * fc.binsY;
   if (launches) *launches = 0;
@@ -186,7 +181,9 @@ BinScratch launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uin
   bin_sort_plan(tiles, &bits, &passes);
   if (launches) *launches = 2 + passes;   // bin_emit, look-back clear, sort passes
   cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
-  k_bin_emit<<<nblocks, 256, 0, s>>>(order, rect, block_flag, n, part, fc.binsX, bs.block_sums + 1, bs.block_sums, bs.capacity,
+  uint32_t words = (uint32_t)block_bits_words(n);
+  if (words * 4u > 32u * 1024u) words = 0;   // a bitmap that does not fit the default shared memory is read through L1 instead
+  k_bin_emit<<<nblocks, 256, words * 4u, s>>>(order, rect, block_bits, words, n, part, fc.binsX, bs.block_sums + 1, bs.block_sums, bs.capacity,
                                      bs.tile_keys, bs.tile_vals, bs.entry_count, sc.ghist, (uint32_t)bits, passes == 2);
   // the entry count lives on the device: a persistent grid sorts whatever it is (no capacity-sized grid or memset)
   launch_sort_pairs(bs.tile_keys, bs.tile_vals, bs.entry_count, bs.capacity, passes, bits, true, sc, s, nullptr, nullptr,

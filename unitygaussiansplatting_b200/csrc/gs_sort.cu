@@ -28,7 +28,6 @@
 
 namespace gs {
 
-constexpr int kSortKPT = 16;   // keys per thread; a tile is THREADS * 16 pairs (4096 or 8192)
 enum : uint32_t { kFlagLocal = 1u << 30, kFlagIncl = 2u << 30, kValMask = (1u << 30) - 1u };
 
 size_t sort_lookback_words(uint32_t capacity, int passes) {
@@ -313,21 +312,25 @@ __global__ void __launch_bounds__(256) k_zero_rows(uint32_t *__restrict__ buf, c
 // ---- ordered compaction of a draw order by a membership mask ------------------------------------------
 // (out_ids, out_keys) = (id, key_table[id]) of the ids of order[0..n) whose bit is set in `mask`, in the order they stand in: the
 // input of a slab's radix sort, compacted out of last frame's draw order.  One status word per 4096-item block, decoupled
-// look-back 32 predecessors wide.  The walk reads the order once (coalesced); per id it first looks at a byte per 128 ids
-// (n/128 bytes: L1-resident) and touches the mask word -- a random L2 access -- only where that group has members at all.
+// look-back 32 predecessors wide (gs_common.cuh).  The walk reads the order once (coalesced); per id it first looks at one bit per 128 ids in
+// a bitmap held in shared memory (a random lookup per draw-order entry through L1 costs ~22 us per 6.1 M entries on B200 however
+// small the table: 32 distinct lines per warp load) and touches the mask word -- a random L2 access -- only where that
+// group has members at all.
 constexpr int kCmpItems = 16;
 constexpr int kCmpBlock = 256 * kCmpItems;
-enum : uint32_t { kCmpFlagLocal = 1u << 30, kCmpFlagIncl = 2u << 30, kCmpValMask = (1u << 30) - 1u };
+enum : uint32_t { kCmpFlagLocal = kLbLocal, kCmpFlagIncl = kLbIncl, kCmpValMask = kLbMask };
 
 __global__ void __launch_bounds__(256) k_compact_order(const uint32_t *__restrict__ order, uint32_t n, const uint32_t *__restrict__ mask,
-                                                       const uint8_t *__restrict__ group_flag,
+                                                       const uint32_t *__restrict__ group_bits, uint32_t bits_words,
                                                        const uint32_t *__restrict__ key_table, uint32_t *__restrict__ out_ids,
                                                        uint32_t *__restrict__ out_keys, volatile uint32_t *status, uint32_t *ticket,
                                                        uint32_t *__restrict__ count_out) {
+  extern __shared__ uint32_t s_bits[];   // the group bitmap (bits_words words), or nothing when it is too large to hold
   __shared__ uint32_t s_w[8];
   __shared__ uint32_t s_block, s_excl;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
+  for (uint32_t i = threadIdx.x; i < bits_words; i += 256) s_bits[i] = __ldg(group_bits + i);
   __syncthreads();
   const uint32_t b = s_block;
   const uint32_t nblocks = (n + kCmpBlock - 1) / kCmpBlock;
@@ -341,7 +344,11 @@ __global__ void __launch_bounds__(256) k_compact_order(const uint32_t *__restric
   uint32_t keepbits = 0;
 #pragma unroll
   for (int i = 0; i < kCmpItems; ++i) {
-    const bool keep = id[i] != 0xFFFFFFFFu && __ldg(group_flag + (id[i] >> 7)) && ((__ldg(mask + (id[i] >> 5)) >> (id[i] & 31u)) & 1u);
+    bool keep = id[i] != 0xFFFFFFFFu;
+    if (keep) {
+      const uint32_t gw = bits_words ? s_bits[id[i] >> 12] : __ldg(group_bits + (id[i] >> 12));
+      keep = ((gw >> ((id[i] >> 7) & 31u)) & 1u) && ((__ldg(mask + (id[i] >> 5)) >> (id[i] & 31u)) & 1u);
+    }
     keepbits |= keep ? (1u << i) : 0u;
   }
   // ranks: slot i of a warp holds 32 consecutive order positions -> ballot prefix inside the slot, running sum over slots
@@ -366,22 +373,7 @@ __global__ void __launch_bounds__(256) k_compact_order(const uint32_t *__restric
     if (lane == 0) status[b] = (b == 0 ? kCmpFlagIncl : kCmpFlagLocal) | total;
     uint32_t excl = 0;
     if (b > 0) {
-      int top = (int)b - 1;
-      while (true) {
-        const int idx = top - (int)lane;
-        uint32_t v;
-        do {
-          v = idx >= 0 ? status[idx] : (uint32_t)kCmpFlagIncl;
-        } while (__any_sync(0xffffffffu, v == 0));
-        const uint32_t incl_mask = __ballot_sync(0xffffffffu, (v & kCmpFlagIncl) != 0);
-        const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
-        uint32_t contrib = ((int)lane <= first) ? (v & kCmpValMask) : 0u;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-        excl += contrib;
-        if (incl_mask) break;
-        top -= 32;
-      }
+      excl = lookback_exclusive(status, b);
       if (lane == 0) status[b] = kCmpFlagIncl | (excl + total);
     }
     if (lane == 0) {
@@ -402,12 +394,14 @@ __global__ void __launch_bounds__(256) k_compact_order(const uint32_t *__restric
 
 size_t compact_status_words(uint32_t n) { return (size_t)(n + kCmpBlock - 1) / kCmpBlock + 1; }
 
-void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mask, const uint8_t *group_flag, const uint32_t *key_table,
+void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mask, const uint32_t *group_bits, const uint32_t *key_table,
                           uint32_t *out_ids, uint32_t *out_keys, uint32_t *status /* compact_status_words(n) */, uint32_t *count_out, cudaStream_t s) {
   if (!n) { cudaMemsetAsync(count_out, 0, 4, s); return; }
   const uint32_t nblocks = (n + kCmpBlock - 1) / kCmpBlock;
   cudaMemsetAsync(status, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
-  k_compact_order<<<nblocks, 256, 0, s>>>(order, n, mask, group_flag, key_table, out_ids, out_keys, status + 1, status, count_out);
+  uint32_t words = (uint32_t)group_bits_words(n);
+  if (words * 4u > 40u * 1024u) words = 0;   // a bitmap that does not fit the default shared memory is read through L1 instead
+  k_compact_order<<<nblocks, 256, words * 4u, s>>>(order, n, mask, group_bits, words, key_table, out_ids, out_keys, status + 1, status, count_out);
 }
 
 // optional per-tile phase trace of the first pass (debug/profiling aid): GS_SORT_TRACE=<file>

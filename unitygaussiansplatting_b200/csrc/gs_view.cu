@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(256) k_calc_distances(AssetView a, float4 row,
     w |= __shfl_xor_sync(0xffffffffu, w, 2);
     w |= __shfl_xor_sync(0xffffffffu, w, 4);
     if ((lane & 7u) == 0 && first < a.n) sl.mask[first >> 5] = w;
-    // one byte per 128 consecutive splats (= this warp's share of the tile): "somebody here belongs to my slab".  Morton-local
-    // splats lie in a narrow depth range, so most groups belong to one or two slabs and the compaction can skip the others
-    // without touching their mask words.
+    // one BIT per 128 consecutive splats (= this warp's share of the tile): "somebody here belongs to my slab" (zeroed before
+    // the launch).  Morton-local splats lie in a narrow depth range, so most groups belong to one or two slabs; the
+    // compaction keeps this bitmap in shared memory and touches a group's mask words only where the bit is set.
     const uint32_t anyw = __ballot_sync(0xffffffffu, nib != 0);
-    if (lane == 0 && first < a.n) sl.group_flag[first >> 7] = anyw ? 1 : 0;
+    if (lane == 0 && anyw && first < a.n) atomicOr(sl.group_bits + (first >> 12), 1u << ((first >> 7) & 31u));
   }
   }  // tile loop
   if (MAXT) {
@@ -294,7 +294,7 @@ template <int SHFMT, bool CULL, bool BC7>
 __global__ void __launch_bounds__(256, (CULL && SHFMT == 3 && !BC7) ? 5 : 1)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
             const uint32_t *__restrict__ selected, uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out,
-            uint8_t *__restrict__ block_flag, Partition part) {
+            uint32_t *__restrict__ block_bits, Partition part) {
   __shared__ __align__(16) uint32_t s_view[256 * 10];
   __shared__ __align__(16) Chunk s_chunk;
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
@@ -359,8 +359,7 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
     __syncthreads();
     if (s_cull) {
       if (idx < a.n) rect_out[idx] = kRectEmpty;
-      if (threadIdx.x == 0) block_flag[blockIdx.x] = 0;
-      return;
+      return;   // block_bits was zeroed before the launch: nothing to set
     }
   }
 
@@ -625,11 +624,12 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
     }
     rect_out[idx] = rect;
   }
-  {  // one byte per 256-splat block: "some splat of this block has a bin rectangle".  The binner walks the draw order and
-     // gathers a splat's rectangle only when its block's flag is set: the flags (n/256 bytes) stay in L1, so the random
+  {  // one BIT per 256-splat block: "some splat of this block has a bin rectangle" (zeroed before the launch, set here).  The
+     // binner walks the draw order and gathers a splat's rectangle only when its block's bit is set; the bitmap (n/2048 bytes:
+     // 3 KB for cfg2) sits in the binner's shared memory, so the per-entry test is a shared-memory read and the random
      // 4-byte gathers are paid for blocks with something to draw only (every other GPU's blocks drop out in a group).
     const int any = __syncthreads_or(rect != kRectEmpty);
-    if (threadIdx.x == 0) block_flag[blockIdx.x] = any ? 1 : 0;
+    if (threadIdx.x == 0 && any) atomicOr(block_bits + (blockIdx.x >> 5), 1u << (blockIdx.x & 31u));
   }
 
   if (CULL) return;   // fused frame: the compositor reads the 48-byte draw records; _SplatViewData is not materialised
@@ -661,6 +661,7 @@ void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *
   const uint32_t grid = tiles < 148u * 8u ? tiles : 148u * 8u;
   const float4 row = make_float4(fc.sort_row[0], fc.sort_row[1], fc.sort_row[2], fc.sort_row[3]);
   SlabArgs none{};
+  if (slabs && slabs->count > 1) cudaMemsetAsync(slabs->group_bits, 0, group_bits_words(a.n) * sizeof(uint32_t), s);
   if (!slabs || slabs->count <= 1) k_calc_distances<0><<<grid, 256, 0, s>>>(a, row, key_table, ghist, none);
   else if (slabs->count <= 2) k_calc_distances<1><<<grid, 256, 0, s>>>(a, row, key_table, ghist, *slabs);
   else if (slabs->count <= 4) k_calc_distances<3><<<grid, 256, 0, s>>>(a, row, key_table, ghist, *slabs);
@@ -670,13 +671,13 @@ void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *
 
 template <bool CULL>
 static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
-                               uint32_t *rect, float4 *draw, uint8_t *block_flag, const Partition &part, cudaStream_t s) {
+                               uint32_t *rect, float4 *draw, uint32_t *block_bits, const Partition &part, cudaStream_t s) {
   const uint32_t grid = (a.n + 255) / 256;
   // BC7 colour (VeryLow preset) is a separate instantiation: the block decode must not cost the other formats registers
 #define GS_VIEW(SH)                                                                                                        \
   do {                                                                                                                    \
-    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_flag, part);  \
-    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_flag, part);               \
+    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, part);  \
+    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, part);               \
   } while (0)
   switch (a.shFmt) {
     case 0: GS_VIEW(0); break;
@@ -689,10 +690,11 @@ static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const 
 }
 
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
-                      uint32_t *rect, float4 *draw, uint8_t *block_flag, bool cull_undrawable, const Partition &part, cudaStream_t s) {
+                      uint32_t *rect, float4 *draw, uint32_t *block_bits, bool cull_undrawable, const Partition &part, cudaStream_t s) {
   if (!a.n) return;
-  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, selected, view, rect, draw, block_flag, part, s);
-  else launch_calc_view_t<false>(a, fc, cutouts, deleted, selected, view, rect, draw, block_flag, part, s);
+  cudaMemsetAsync(block_bits, 0, block_bits_words(a.n) * sizeof(uint32_t), s);
+  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, part, s);
+  else launch_calc_view_t<false>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, part, s);
 }
 
 }  // namespace gs
