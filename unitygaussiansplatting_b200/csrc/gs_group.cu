@@ -57,7 +57,23 @@ struct Member {
 
 }  // namespace
 
+// Peer-to-peer order exchange (one process per GPU): every process maps every peer's two order buffers and flag words
+// through CUDA IPC; after its slab sort a GPU stores its slab straight into all peers' NEW order buffer over NVLink and
+// raises a flag there; nobody calls into NCCL, nothing is staged or unpacked.
+struct PeerLink {
+  bool tried = false, ready = false;
+  GsAsset *asset = nullptr;
+  uint32_t *buf[2] = {nullptr, nullptr};                       // local: the asset's two order buffers, by fixed index
+  uint32_t *peer_buf[2][GS_GROUP_MAX_GPUS] = {};               // the same two buffers of every rank (own rank: local)
+  uint32_t *flags = nullptr, *peer_flags[GS_GROUP_MAX_GPUS] = {};   // flags[c] = last sort frame whose slab rank c delivered here
+  uint32_t *d_done = nullptr;                                   // block counter of the push kernel
+  void *opened[3 * GS_GROUP_MAX_GPUS] = {};
+  int n_opened = 0;
+  uint32_t sort_frames = 0;
+};
+
 struct GsGroup {
+  PeerLink link;
   uint32_t size = 0;
   std::vector<Member> m;
   bool emulate = false, use_nccl = false;
@@ -219,6 +235,115 @@ int exchange_allgather(GsGroup *g, uint8_t *const *bufs, size_t slot_bytes, cons
   return exchange_add(g, bufs, off, cnt);   // device copies of the filled part of every slot
 }
 
+struct PushArgs { uint32_t *dst[GS_GROUP_MAX_GPUS]; uint32_t *flag[GS_GROUP_MAX_GPUS]; uint32_t npeers; };
+
+// Stores this GPU's sorted slab into every peer's order buffer (remote stores over NVLink, coalesced 4-byte lanes), then --
+// once every block's stores are fenced system-wide -- the last block raises this rank's flag on every peer.
+__global__ void __launch_bounds__(512) k_push_slab(const uint32_t *__restrict__ src, uint32_t cnt, PushArgs a, uint32_t tag, uint32_t *done) {
+  for (uint32_t p = 0; p < a.npeers; ++p) {
+    uint32_t *dst = a.dst[p];
+    for (uint32_t i = blockIdx.x * 512 + threadIdx.x; i < cnt; i += gridDim.x * 512) dst[i] = __ldg(src + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if (threadIdx.x < a.npeers) *reinterpret_cast<volatile uint32_t *>(a.flag[threadIdx.x]) = tag;
+    if (threadIdx.x == 0) *done = 0;
+  }
+}
+
+// Waits until every other rank's flag here has reached `tag` (their slabs are in this GPU's order buffer).  A peer that never
+// delivers would hang the stream: after ~2 s the kernel gives up and records it (flags[count] != 0 -> the frame is void).
+__global__ void k_wait_slabs(volatile uint32_t *flags, uint32_t count, uint32_t self, uint32_t tag) {
+  const uint32_t c = threadIdx.x;
+  if (c < count && c != self) {
+    const long long t0 = clock64();
+    while ((int32_t)(flags[c] - tag) < 0) {
+      __nanosleep(200);
+      if (clock64() - t0 > 4000000000ll) { flags[count] = 1u; break; }
+    }
+  }
+  __threadfence_system();
+}
+
+// Collective (every process of the group, same call sequence).  On any failure anywhere the link stays off and the NCCL
+// exchange is used.
+int peer_link_setup(GsGroup *g, GsAsset *as) {
+  PeerLink &k = g->link;
+  k.tried = true;
+  Member &mb = g->m[0];
+  GsContext *ctx = mb.ctx;
+  const uint32_t G = g->size, n = as->av.n;
+  const NcclApi &nc = nccl_api();
+  struct Pack { cudaIpcMemHandle_t h[3]; uint32_t ok; uint32_t pad[15]; };
+  static_assert(sizeof(Pack) == 3 * 64 + 64, "pack layout");
+  Pack mine;
+  memset(&mine, 0, sizeof(mine));
+  bool ok = true;
+  if (!as->order_alt) ok = cudaMalloc(&as->order_alt, (size_t)n * 4 + 16) == cudaSuccess;
+  if (ok && !k.flags) ok = cudaMalloc(&k.flags, 64 * 4) == cudaSuccess && cudaMalloc(&k.d_done, 16) == cudaSuccess;
+  if (ok) {
+    cudaMemsetAsync(k.flags, 0, 64 * 4, ctx->stream);
+    cudaMemsetAsync(k.d_done, 0, 16, ctx->stream);
+    cudaMemsetAsync(as->order_alt, 0, (size_t)n * 4, ctx->stream);
+    ok = cudaIpcGetMemHandle(&mine.h[0], as->order) == cudaSuccess && cudaIpcGetMemHandle(&mine.h[1], as->order_alt) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine.h[2], k.flags) == cudaSuccess;
+  }
+  cudaGetLastError();
+  mine.ok = ok ? 1u : 0u;
+  Pack *d_all = nullptr;
+  std::vector<Pack> all(G);
+  if (cudaMalloc(&d_all, sizeof(Pack) * G) != cudaSuccess) return fail(ctx, GS_ERR_OUT_OF_MEMORY, "peer link: device allocation failed");
+  cudaMemcpyAsync(d_all + mb.rank, &mine, sizeof(Pack), cudaMemcpyHostToDevice, ctx->stream);
+  ncclResult_t r = nc.AllGather(d_all + mb.rank, d_all, sizeof(Pack), ncclUint8, mb.comm, ctx->stream);
+  if (r != ncclSuccess) { cudaFree(d_all); return fail_nccl(ctx, r, "ncclAllGather(peer handles)"); }
+  cudaMemcpyAsync(all.data(), d_all, sizeof(Pack) * G, cudaMemcpyDeviceToHost, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaFree(d_all); return fail(ctx, GS_ERR_CUDA, "peer link: handle exchange failed"); }
+  bool everyone = true;
+  for (uint32_t c = 0; c < G; ++c) everyone &= all[c].ok != 0;
+  uint32_t opened_ok = everyone ? 1u : 0u;
+  if (everyone) {
+    k.buf[0] = as->order; k.buf[1] = as->order_alt;
+    for (uint32_t c = 0; c < G && opened_ok; ++c) {
+      if (c == mb.rank) { k.peer_buf[0][c] = k.buf[0]; k.peer_buf[1][c] = k.buf[1]; k.peer_flags[c] = k.flags; continue; }
+      void *ptr[3] = {nullptr, nullptr, nullptr};
+      for (int j = 0; j < 3 && opened_ok; ++j) {
+        if (cudaIpcOpenMemHandle(&ptr[j], all[c].h[j], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened_ok = 0; cudaGetLastError(); break; }
+        k.opened[k.n_opened++] = ptr[j];
+      }
+      k.peer_buf[0][c] = (uint32_t *)ptr[0]; k.peer_buf[1][c] = (uint32_t *)ptr[1]; k.peer_flags[c] = (uint32_t *)ptr[2];
+    }
+  }
+  // second round: did everybody manage to map everybody?
+  uint32_t *d_ok = reinterpret_cast<uint32_t *>(d_all);
+  cudaMemcpyAsync(d_ok + mb.rank, &opened_ok, 4, cudaMemcpyHostToDevice, ctx->stream);
+  r = nc.AllGather(d_ok + mb.rank, d_ok, 4, ncclUint8, mb.comm, ctx->stream);
+  std::vector<uint32_t> oks(G, 0);
+  if (r == ncclSuccess) cudaMemcpyAsync(oks.data(), d_ok, 4 * G, cudaMemcpyDeviceToHost, ctx->stream);
+  const bool synced = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+  cudaFree(d_all);
+  if (r != ncclSuccess || !synced) return fail(ctx, GS_ERR_CUDA, "peer link: confirmation exchange failed");
+  bool all_ok = true;
+  for (uint32_t c = 0; c < G; ++c) all_ok &= oks[c] != 0;
+  if (all_ok) { k.ready = true; k.asset = as; k.sort_frames = 0; }
+  return GS_OK;
+}
+
+void peer_link_release(GsGroup *g) {
+  PeerLink &k = g->link;
+  if (!g->m.empty() && g->m[0].ctx) { cudaSetDevice(g->m[0].ctx->device); cudaStreamSynchronize(g->m[0].ctx->stream); }
+  for (int i = 0; i < k.n_opened; ++i) if (k.opened[i]) cudaIpcCloseMemHandle(k.opened[i]);
+  k.n_opened = 0;
+  cudaFree(k.flags); cudaFree(k.d_done);
+  k.flags = k.d_done = nullptr;
+  k.ready = false;
+  cudaGetLastError();
+}
+
 void balance_rows(const uint32_t *cost, uint32_t rows, uint32_t parts, uint32_t *bounds) {
   // every row also carries a fixed share (its tiles are launched, its pixels stored) so that empty rows are not free
   uint64_t sum = 0;
@@ -346,6 +471,7 @@ int gs_group_create(const int *devices, uint32_t n, uint32_t flags, GsGroup **ou
 
 void gs_group_destroy(GsGroup *g) {
   if (!g) return;
+  peer_link_release(g);
   for (Member &mb : g->m) member_free(mb);
   delete g;
 }
@@ -500,7 +626,18 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
     cap = (cap + 3u) & ~3u;
     static int ag_env = -1;
     if (ag_env < 0) { const char *e = getenv("GS_GROUP_ORDER_ALLGATHER"); ag_env = (e && e[0] == '0') ? 0 : 1; }
-    const bool use_gather = G > 1 && ag_env && g->xfer == 0 && (uint64_t)cap * G <= (uint64_t)N + (uint64_t)N / 2 + 64u * G;
+    // one process per GPU: slabs go peer to peer (set up on the first sorted frame; GS_GROUP_P2P=0 keeps NCCL)
+    static int p2p_env = -1;
+    if (p2p_env < 0) { const char *e = getenv("GS_GROUP_P2P"); p2p_env = (e && e[0] == '0') ? 0 : 1; }
+    if (G > 1 && g->use_nccl && L == 1 && p2p_env && !g->link.tried) { if ((rc = peer_link_setup(g, assets[0]))) return rc; }
+    const bool use_p2p = G > 1 && L == 1 && g->link.ready && g->link.asset == assets[0];
+    uint32_t *p2p_new = nullptr;
+    int p2p_idx = 0;
+    if (use_p2p) {   // the two order buffers alternate: last frame's order is read, the other one is assembled
+      p2p_idx = assets[0]->order == g->link.buf[0] ? 1 : 0;
+      p2p_new = g->link.buf[p2p_idx];
+    }
+    const bool use_gather = !use_p2p && G > 1 && ag_env && g->xfer == 0 && (uint64_t)cap * G <= (uint64_t)N + (uint64_t)N / 2 + 64u * G;
     if (use_gather) {
       for (size_t i = 0; i < L; ++i) {
         Member &mb = g->m[i];
@@ -529,8 +666,22 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
         launch_compact_order(as->order, N, as->slab_mask, as->slab_group_bits, as->key_table, as->order_tmp, as->keys, mb.d_cmp_status, mb.d_slab_count,
                              ctx->stream);
         launch_sort_pairs(as->keys, as->order_tmp, mb.d_slab_count, cnt, 4, 8, true, ctx->sort, ctx->stream, nullptr, nullptr, true,
-                          as->keys + off, use_gather ? mb.d_gather + (size_t)mb.rank * cap : as->order + off);
+                          as->keys + off, use_p2p ? p2p_new + off : use_gather ? mb.d_gather + (size_t)mb.rank * cap : as->order + off);
         ctx->launches += 5;
+      }
+      if (use_p2p) {
+        PeerLink &k = g->link;
+        const uint32_t tag = ++k.sort_frames;
+        PushArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        for (uint32_t c = 0; c < G; ++c)
+          if (c != mb.rank) { pa.dst[pa.npeers] = k.peer_buf[p2p_idx][c] + off; pa.flag[pa.npeers] = k.peer_flags[c] + mb.rank; ++pa.npeers; }
+        k_push_slab<<<148, 512, 0, ctx->stream>>>(p2p_new + off, cnt, pa, tag, k.d_done);
+        k_wait_slabs<<<1, 32, 0, ctx->stream>>>(k.flags, G, mb.rank, tag);
+        ctx->launches += 2;
+        // from here on the assembled buffer IS the draw order; last frame's becomes the next frame's target
+        as->order_alt = as->order;
+        as->order = p2p_new;
       }
       GS_CUDA_TRY(ctx, cudaGetLastError());
       if (timing) cudaEventRecord(mb.tev[GT_SORT], ctx->stream);
@@ -543,7 +694,9 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
       std::vector<uint8_t *> bufs(L);
       size_t off[GS_GROUP_MAX_GPUS], cnt[GS_GROUP_MAX_GPUS];
       for (uint32_t c = 0; c < G; ++c) { off[c] = (size_t)g->slab_off[c] * 4; cnt[c] = (size_t)g->slab_cnt[c] * 4; }
-      if (use_gather) {
+      if (use_p2p) {
+        // delivered by k_push_slab / awaited by k_wait_slabs above
+      } else if (use_gather) {
         for (size_t i = 0; i < L; ++i) bufs[i] = reinterpret_cast<uint8_t *>(g->m[i].d_gather);
         if ((rc = exchange_allgather(g, bufs.data(), (size_t)cap * 4, cnt))) return rc;
         SlabLayout lay;

@@ -72,6 +72,7 @@ struct GsAsset {
   uint32_t *block_bits = nullptr;  // bit j: some splat of block j (256 splats) got a bin rectangle from the last view-calc
   // group path only (allocated by gs_group_*): slab membership (bit per splat, byte per 128), compaction output / sort ping-pong payload
   uint32_t *slab_mask = nullptr, *order_tmp = nullptr;
+  uint32_t *order_alt = nullptr;   // peer-to-peer order exchange: `order` and `order_alt` alternate as last / new draw order
   uint32_t *slab_group_bits = nullptr;
   float4 *draw = nullptr;  // raster-ready 48-byte records of the drawable splats
   bool view_valid = false;   // the full 40-byte _SplatViewData buffer is current (gs_calc_view)

@@ -214,11 +214,20 @@ class GaussianSplatGroup:
 
     def close(self):
         if self.handle:
-            for i in range(self.local_count):
-                if self._assets[i]:
-                    self._lib.gs_asset_destroy(self._assets[i])
-                    self._assets[i] = None
-            self._lib.gs_group_destroy(self.handle)
+            def free_assets():
+                for i in range(self.local_count):
+                    if self._assets[i]:
+                        self._lib.gs_asset_destroy(self._assets[i])
+                        self._assets[i] = None
+            if getattr(self, "_owner_ctx", None) is not None:
+                # joined group: the context is the caller's and outlives the group; the group goes first so that the peers'
+                # mappings of this process's order buffers are closed before the buffers are freed
+                self._lib.gs_group_destroy(self.handle)
+                free_assets()
+            else:
+                # created group: the library owns the contexts, so the assets (which live on them) go first
+                free_assets()
+                self._lib.gs_group_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
