@@ -593,7 +593,13 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
       }
     }
     if (timing) cudaEventRecord(mb.tev[GT_DIST], ctx->stream);
-    if (!view_late && (rc = enqueue_view(i, mb.ev_begin))) return rc;
+    // view-calc starts right behind the distance kernel (started together, its 24 k blocks crowd the distance kernel out:
+    // 63 instead of 32 us at N = 8) and so runs under the host's wait for the slab table, the sort's tails and the exchange
+    if (!view_late) {
+      cudaEvent_t after = mb.ev_begin;
+      if (do_sort_flag) { GS_CUDA_TRY(ctx, cudaEventRecord(mb.ev_produced, ctx->stream)); after = mb.ev_produced; }
+      if ((rc = enqueue_view(i, after))) return rc;
+    }
   }
 
   // ---- slab sizes: the one host wait of the frame (the GPUs are busy with view-calc) ----------------------------------
@@ -760,8 +766,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
       if (timing) cudaEventRecord(mb.tev[GT_VIEWWAIT], ctx->stream);
       rec(ctx, EV_VIEW1);
       if ((rc = do_render(ctx, as, fc, opt, d_rt, pitch, fmt))) return rc;
-      launch_row_costs(ctx->bin.tile_cost, ntx, g->bounds[mb.rank], g->bounds[mb.rank + 1], mb.d_row_cost, ctx->stream);
-      ctx->launches += 1;
+      ctx->launches += 1;   // k_row_costs, launched on the transfer stream below
     } else if (timing) {
       cudaEventRecord(mb.tev[GT_VIEWWAIT], ctx->stream);
     }
@@ -775,6 +780,8 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
     GS_CUDA_TRY(mb.ctx, cudaSetDevice(mb.ctx->device));
     GS_CUDA_TRY(mb.ctx, cudaEventRecord(mb.ev_raster, mb.ctx->stream));
     GS_CUDA_TRY(mb.ctx, cudaStreamWaitEvent(mb.xfer, mb.ev_raster, 0));
+    if (g->bounds[mb.rank + 1] > g->bounds[mb.rank] || G == 1)   // the measured cost of my rows, for the balancer two frames on
+      launch_row_costs(mb.ctx->bin.tile_cost, ntx, g->bounds[mb.rank], g->bounds[mb.rank + 1], mb.d_row_cost, mb.xfer);
   }
   if (G > 1) {
     size_t off[GS_GROUP_MAX_GPUS], cnt[GS_GROUP_MAX_GPUS], coff[GS_GROUP_MAX_GPUS], ccnt[GS_GROUP_MAX_GPUS];

@@ -31,10 +31,7 @@ constexpr int kBinBlock = 256 * kBinItems;    // ranks per block
 // ---- 1. count + scan + emit in ONE pass ---------------------------------------------------------
 // Blocks take their index by atomic ticket, publish their entry total with a LOCAL flag, resolve
 // their exclusive offset by a warp-parallel decoupled look-back (32 predecessors per probe, gs_common.cuh), then
-// emit (tile id, splat id) entries in depth order.  Emission is warp-cooperative: the 32 ranks a warp
-// holds for one item slot own one contiguous output range; lane x of the warp writes entry x of that
-// range (owner found by a 5-step shuffle search over the lanes' prefix sums), so every store is a
-// full coalesced line regardless of how many tiles each splat touches.
+// emit (tile id, splat id) entries in depth order.
 enum : uint32_t { kBinFlagLocal = kLbLocal, kBinFlagIncl = kLbIncl, kBinValMask = kLbMask };
 
 __device__ __forceinline__ uint32_t entry_tile(uint32_t e, uint32_t r, const Partition &p, uint32_t tilesX) {
@@ -56,6 +53,8 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
   __shared__ uint32_t s_w[8];
   __shared__ uint32_t s_block, s_excl;
   __shared__ uint32_t s_dh[512];   // digit histograms of the two sort passes over the tile ids we emit
+  __shared__ uint2 s_items[kBinBlock];     // per warp: its drawable ranks, squeezed together in order
+  __shared__ uint32_t s_pre[kBinBlock];
   const uint32_t nblocks = (n + kBinBlock - 1) / kBinBlock;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
@@ -64,16 +63,14 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
   const uint32_t dmask = (1u << digit_bits) - 1u;
   __syncthreads();
   const uint32_t b = s_block;
-  // warp-striped ranks: item i of lane l is rank wbase + i*32 + l (coalesced loads, and the 32 lanes of one
-  // item slot hold 32 consecutive ranks == one contiguous output range)
+  // warp-striped ranks: item i of lane l is rank wbase + i*32 + l (coalesced loads; the warp's 256 ranks are consecutive)
   const uint32_t wbase = b * kBinBlock + warp * (32 * kBinItems) + lane;
-  uint32_t id[kBinItems], rc[kBinItems], pre[kBinItems];
+  uint32_t id[kBinItems], rc[kBinItems];
 #pragma unroll
   for (int i = 0; i < kBinItems; ++i) {
     const uint32_t r = wbase + i * 32;
     id[i] = (r < n) ? __ldg(order + r) : 0xFFFFFFFFu;
   }
-#pragma unroll
   // the rectangle of a splat is a random 4-byte gather; the view kernel's per-block bits (in shared memory) say where there
   // is nothing to fetch
 #pragma unroll
@@ -84,19 +81,40 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
       if ((bw >> ((id[i] >> 8) & 31u)) & 1u) rc[i] = __ldg(rect + id[i]);
     }
   }
-  uint32_t wtot[kBinItems], wsum = 0;
+  // Most ranks have nothing to emit (70 % of cfg2's splats draw nothing; in a group of G only 1/G of the rest is ours).
+  // The warp first squeezes its drawable ranks, in order, into shared memory, and everything below -- entry counts, prefix
+  // scans, the emission loop -- runs over those K <= 256 items in chunks of 32 instead of over 8 sparse slots.
+  uint2 *w_items = s_items + warp * (32 * kBinItems);     // (splat id, rect)
+  uint32_t *w_pre = s_pre + warp * (32 * kBinItems);      // exclusive prefix of the item's entries inside its chunk
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t K = 0;
 #pragma unroll
   for (int i = 0; i < kBinItems; ++i) {
-    const uint32_t c = rect_entries(rc[i], part);
-    uint32_t inc = c;
+    const bool has = rect_entries(rc[i], part) != 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, has);
+    if (has) w_items[K + __popc(bal & lt)] = make_uint2(id[i], rc[i]);
+    K += __popc(bal);
+  }
+  __syncwarp();
+  const uint32_t nchunks = (K + 31) >> 5;
+  uint32_t ctot[kBinItems];   // entries of chunk j (warp-uniform)
+  uint32_t wsum = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= (uint32_t)o) inc += t;
+  for (int j = 0; j < kBinItems; ++j) {
+    ctot[j] = 0;
+    if ((uint32_t)j < nchunks) {
+      const uint32_t k = j * 32 + lane;
+      const uint32_t c = k < K ? rect_entries(w_items[k].y, part) : 0u;
+      uint32_t inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+      }
+      w_pre[k] = inc - c;
+      ctot[j] = __shfl_sync(0xffffffffu, inc, 31);
+      wsum += ctot[j];
     }
-    pre[i] = inc - c;
-    wtot[i] = __shfl_sync(0xffffffffu, inc, 31);
-    wsum += wtot[i];
   }
   if (lane == 0) s_w[warp] = wsum;
   __syncthreads();
@@ -126,10 +144,17 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
     }
   }
   __syncthreads();
+  // Emission is warp-cooperative: the 32 items of a chunk own one contiguous output range; lane x of the warp writes entry x
+  // of that range (owner found by a 5-step shuffle search over the lanes' prefix sums), so every store is a full coalesced
+  // line regardless of how many bins each splat touches.
   uint32_t off = s_excl + woff;
 #pragma unroll
-  for (int i = 0; i < kBinItems; ++i) {
-    const uint32_t T = wtot[i];
+  for (int j = 0; j < kBinItems; ++j) {
+    if ((uint32_t)j >= nchunks) break;
+    const uint32_t k = j * 32 + lane;
+    const uint2 it = k < K ? w_items[k] : make_uint2(0xFFFFFFFFu, kRectEmpty);
+    const uint32_t pre = k < K ? w_pre[k] : 0xFFFFFFFFu;   // lanes past the end never own an entry
+    const uint32_t T = ctot[j];
     for (uint32_t e0 = 0; e0 < T; e0 += 32) {
       const uint32_t x = e0 + lane;
       // owner = last lane whose exclusive prefix is <= x
@@ -137,12 +162,12 @@ __global__ void __launch_bounds__(256) k_bin_emit(const uint32_t *__restrict__ o
 #pragma unroll
       for (int step = 0; step < 5; ++step) {
         const uint32_t mid = (lo + hi + 1) >> 1;
-        const uint32_t pm = __shfl_sync(0xffffffffu, pre[i], mid);
+        const uint32_t pm = __shfl_sync(0xffffffffu, pre, mid);
         if (pm <= x) lo = mid; else hi = mid - 1;
       }
-      const uint32_t opre = __shfl_sync(0xffffffffu, pre[i], lo);
-      const uint32_t orc = __shfl_sync(0xffffffffu, rc[i], lo);
-      const uint32_t oid = __shfl_sync(0xffffffffu, id[i], lo);
+      const uint32_t opre = __shfl_sync(0xffffffffu, pre, lo);
+      const uint32_t orc = __shfl_sync(0xffffffffu, it.y, lo);
+      const uint32_t oid = __shfl_sync(0xffffffffu, it.x, lo);
       const uint32_t o = off + x;
       if (x < T && o < capacity) {
         const uint32_t tile = entry_tile(x - opre, orc, part, tilesX);
