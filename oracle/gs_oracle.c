@@ -550,6 +550,14 @@ void gso_calc_view(const GsoAsset *a, const GsoFrame *f, GsoView *view, int thre
 /* ------------------------------------------------------------------ draw + blend */
 static inline float round_h(float v) { return gso_f16tof32(gso_f32tof16(v)); }
 
+/* band t covers rows [H*t/bands, H*(t+1)/bands): the band of row y is the largest t with H*t/bands <= y */
+static inline int band_of_row(int32_t y, int bands, uint32_t H) {
+  int t = (int)(((uint64_t)y * (uint64_t)bands) / H);
+  while (t + 1 < bands && (int32_t)((uint64_t)H * (uint64_t)(t + 1) / (uint64_t)bands) <= y) ++t;
+  while (t > 0 && (int32_t)((uint64_t)H * (uint64_t)t / (uint64_t)bands) > y) --t;
+  return t;
+}
+
 typedef struct DrawRec { /* per-splat constants of the draw, computed once (phase 1) */
   float cx, cy, i1x, i1y, i2x, i2y, cr, cg, cb, ca;
   int32_t x0, x1, y0, y1; /* pixel rectangle to visit; x0 >= x1 marks "nothing to draw" */
@@ -602,14 +610,13 @@ void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint
   if ((uint32_t)bands > H) bands = (int)H;
   if (bands < 1) bands = 1;
   uint64_t *band_start = (uint64_t *)calloc((size_t)bands + 1, sizeof(uint64_t));
-  /* band t covers rows [H*t/bands, H*(t+1)/bands); first/last band of a record by scanning (bands is small) */
   for (uint32_t k = 0; k < n; ++k) {
     const DrawRec *r = &recs[k];
     if (r->x0 >= r->x1) continue;
-    for (int t = 0; t < bands; ++t) {
-      const int32_t row0 = (int32_t)((uint64_t)H * t / bands), row1 = (int32_t)((uint64_t)H * (t + 1) / bands);
-      if (r->y0 < row1 && r->y1 > row0) band_start[t + 1]++;
-    }
+    int t0, t1;
+    t0 = band_of_row(r->y0, bands, H);
+    t1 = band_of_row(r->y1 - 1, bands, H);
+    for (int t = t0; t <= t1; ++t) band_start[t + 1]++;
   }
   for (int t = 0; t < bands; ++t) band_start[t + 1] += band_start[t];
   uint32_t *band_list = (uint32_t *)malloc((size_t)(band_start[bands] ? band_start[bands] : 1) * sizeof(uint32_t));
@@ -618,10 +625,10 @@ void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint
   for (uint32_t k = 0; k < n; ++k) {            /* in draw order, so every band's list is in draw order */
     const DrawRec *r = &recs[k];
     if (r->x0 >= r->x1) continue;
-    for (int t = 0; t < bands; ++t) {
-      const int32_t row0 = (int32_t)((uint64_t)H * t / bands), row1 = (int32_t)((uint64_t)H * (t + 1) / bands);
-      if (r->y0 < row1 && r->y1 > row0) band_list[fill[t]++] = k;
-    }
+    int t0, t1;
+    t0 = band_of_row(r->y0, bands, H);
+    t1 = band_of_row(r->y1 - 1, bands, H);
+    for (int t = t0; t <= t1; ++t) band_list[fill[t]++] = k;
   }
   free(fill);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)

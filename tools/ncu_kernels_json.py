@@ -26,7 +26,12 @@ def main():
     for d in data:
         if len(d) != len(hdr):
             continue
-        name = d[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("gs::", "").split("<")[0]
+        full = d[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("gs::", "")
+        name = full.split("<")[0]
+        if name == "k_onesweep" and "<" in full:   # <BITS, GATHER, THREADS, PERSIST, KPT>: the persistent variant is the bin sort, not the depth sort
+            targs = [a.strip() for a in full[full.index("<") + 1:full.rindex(">")].split(",")]
+            if len(targs) >= 4 and targs[3] in ("1", "true", "(bool)1"):
+                name = "k_onesweep_binsort"
         a = acc[name]
 
         def val(m, table):

@@ -244,12 +244,15 @@ k_onesweep(const uint32_t *__restrict__ src_k, const uint32_t *__restrict__ src_
     const uint32_t m = match_digit<BITS>(d);
     // every lane reads its digit's running count (lanes of one digit read one word: a broadcast), then the lowest lane of
     // each digit group -- the one with no equal-digit lane below it -- stores the new count: a predicated store, no
-    // branch, no shuffle.  Shared-memory accesses of one warp execute in program order, so round i+1 sees round i's store.
+    // branch, no shuffle.  The __syncwarp() orders round i's store before round i+1's loads for the memory model (and for
+    // compute-sanitizer's racecheck, which flagged the version without it); it costs nothing measurable.
     const uint32_t below = __popc(m & lt_mask);
     const uint32_t prev = s_whist[warp][d];
+    __syncwarp();
     if (below == 0) s_whist[warp][d] = prev + __popc(m);
     const uint32_t r = prev + below;
     if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
+    __syncwarp();
   }
   __syncthreads();
   GS_TRACE(3);
