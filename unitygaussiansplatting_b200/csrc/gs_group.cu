@@ -503,6 +503,12 @@ int gs_group_sync(GsGroup *g) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(mb.xfer);
     if (e != cudaSuccess && rc == GS_OK) rc = fail_cuda(mb.ctx, e, "cudaStreamSynchronize(aux/xfer)", __FILE__, __LINE__);
     mb.image_pending = false;
+    if (g->link.ready && rc == GS_OK) {   // a peer that never delivered its slab made k_wait_slabs give up: the frame is void
+      uint32_t bad = 0;
+      e = cudaMemcpy(&bad, g->link.flags + g->size, 4, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = fail_cuda(mb.ctx, e, "cudaMemcpy(peer flags)", __FILE__, __LINE__);
+      else if (bad) rc = fail(mb.ctx, GS_ERR_CUDA, "peer-to-peer order exchange timed out: a process of the group did not deliver its slab");
+    }
     const int r = gs_sync(mb.ctx);
     if (r != GS_OK && rc == GS_OK) rc = r;
   }
