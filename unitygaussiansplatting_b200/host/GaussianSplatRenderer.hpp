@@ -99,4 +99,66 @@ class GaussianSplatRenderer {
   int m_FrameCounter = 0;
 };
 
+// The same renderer on several GPUs of one box, one process driving all of them (gs_group_create / gs_group_frame):
+// identical knobs; every non-null image receives the complete frame, bit-identical to what one GPU renders.
+class GaussianSplatRendererGroup {
+ public:
+  float m_SplatScale = 1.0f, m_OpacityScale = 1.0f;
+  int m_SHOrder = 3;
+  bool m_SHOnly = false;
+  int m_SortNthFrame = 1;
+  Matrix4x4 localToWorldMatrix{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};
+  Matrix4x4 worldToLocalMatrix{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};
+  GsRenderOptions options{};
+
+  ~GaussianSplatRendererGroup() { OnDisable(); }
+
+  bool OnEnable(const GsAssetDesc &asset, const std::vector<int> &cudaDevices, uint32_t flags = 0) {
+    OnDisable();
+    if (!ok(gs_group_create(cudaDevices.data(), (uint32_t)cudaDevices.size(), flags, &m_Group))) return false;
+    m_Assets.assign(gs_group_local_count(m_Group), nullptr);
+    if (!ok(gs_group_asset_upload(m_Group, &asset, m_Assets.data()))) return false;
+    m_FrameCounter = 0;
+    return true;
+  }
+  void OnDisable() {
+    for (GsAsset *a : m_Assets) if (a) gs_asset_destroy(a);   // the library owns the contexts: assets go first
+    m_Assets.clear();
+    if (m_Group) gs_group_destroy(m_Group);
+    m_Group = nullptr;
+  }
+  // rts[i]: the image of local member i (device or host memory) or nullptr
+  bool SortAndRenderSplats(const CameraState &cam, GsImage *const *rts) {
+    const int doSort = (m_FrameCounter % (m_SortNthFrame > 0 ? m_SortNthFrame : 1)) == 0;
+    ++m_FrameCounter;
+    GsFrameParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    std::memcpy(fp.mat_object_to_world, localToWorldMatrix.m, 64);
+    std::memcpy(fp.mat_world_to_object, worldToLocalMatrix.m, 64);
+    std::memcpy(fp.mat_view, cam.worldToCameraMatrix.m, 64);
+    std::memcpy(fp.mat_proj_gpu, cam.gpuProjectionMatrix.m, 64);
+    fp.screen_w = cam.pixelWidth;
+    fp.screen_h = cam.pixelHeight;
+    std::memcpy(fp.cam_pos_world, cam.position, 12);
+    fp.splat_scale = m_SplatScale;
+    fp.opacity_scale = m_OpacityScale;
+    fp.sh_order = (uint32_t)m_SHOrder;
+    fp.sh_only = m_SHOnly ? 1u : 0u;
+    return ok(gs_group_frame(m_Group, m_Assets.data(), &fp, &options, doSort, rts));
+  }
+  bool Sync() { return ok(gs_group_sync(m_Group)); }
+  GsGroup *group() const { return m_Group; }
+  GsAsset *asset(size_t i) const { return m_Assets[i]; }
+
+ private:
+  bool ok(int rc) const {
+    if (rc == GS_OK) return true;
+    std::fprintf(stderr, "GaussianSplatRendererGroup: %s (%d)\n", gs_last_error(m_Group ? gs_group_context(m_Group, 0) : nullptr), rc);
+    return false;
+  }
+  GsGroup *m_Group = nullptr;
+  std::vector<GsAsset *> m_Assets;
+  int m_FrameCounter = 0;
+};
+
 }  // namespace GaussianSplatting
