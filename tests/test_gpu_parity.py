@@ -355,3 +355,36 @@ def test_selected_splats(g, O, ctx):
     for i in range(3):
         assert np.array_equal(rts[i], rt)
     grp.close()
+
+
+def test_orthographic_projection(g, O, ctx):
+    """gs_frame accepts any GPU projection matrix.  With an orthographic one clip.w == 1, so the fused kernel's chunk / splat
+    culls must take the view depth from the model-view matrix (not from clip.w): the fused frame has to equal both the staged
+    path (gs_calc_view + gs_render, which culls nothing) and the oracle."""
+    import ctypes as C
+    from unitygaussiansplatting_b200 import _native as N
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 40000, 0x5EED0094, "Medium")
+    cam = camera(g, 400, 300)
+    r = g.GaussianSplatRenderer(asset, ctx)
+    fp = r.frame_params(cam)
+    half_h, n_, f_ = 4.0, 0.3, 100.0
+    half_w = half_h * 400 / 300
+    ortho = np.array([[1 / half_w, 0, 0, 0], [0, 1 / half_h, 0, 0], [0, 0, -2 / (f_ - n_), -(f_ + n_) / (f_ - n_)], [0, 0, 0, 1]], np.float64)
+    ortho[1, :] *= -1.0                                  # render-texture flip, as GL.GetGPUProjectionMatrix(.., true) does
+    ortho[2, :] = ortho[2, :] * -0.5 + ortho[3, :] * 0.5  # reversed z
+    C.memmove(C.addressof(fp) + N.GsFrameParams.mat_proj_gpu.offset, g.camera.colmajor(ortho).ctypes.data, 64)
+    rt = np.zeros((300, 400, 4), np.float16)
+    r.SortAndRenderSplats(cam, rt=rt, fp=fp)
+    ref = O.frame(asset, fp, threads=O.max_threads())
+    assert rt.any()
+    assert np.array_equal(r.readback_order(), ref["order"])
+    assert np.array_equal(rt.astype(np.float32), ref["rt"])
+    lib = N.native()
+    N.check(ctx.handle, lib.gs_calc_view(ctx.handle, r._asset, C.byref(fp)))
+    assert np.array_equal(r.readback_view(), ref["view"])
+    rt2 = np.zeros_like(rt)
+    opt = r._options()
+    im = g.renderer._image(rt2, 400, 300)
+    N.check(ctx.handle, lib.gs_render(ctx.handle, r._asset, C.byref(fp), C.byref(opt), C.byref(im)))
+    assert np.array_equal(rt2, rt)
+    r.Dispose()

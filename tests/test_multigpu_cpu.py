@@ -60,7 +60,7 @@ def _worker(rank, world, port, q):
     full = O.frame(asset, fp)["rt"].astype(np.float16)                     # stands in for the rank's renderer
     part = BandPartition(H, world, rank, band_rows=2)
     mine = np.zeros((part.rows_per_partition, W, 4), np.float16)
-    for k in range(part.own_tile_rows()):                                  # band-packed send buffer: own tile row k -> rows [16k,16k+16)
+    for k in range(part.own_tile_rows()):                                  # band-packed send buffer: own 64-pixel row k -> rows [64k, 64k+64)
         ty = part.kth_own_row(k)
         rows = full[ty * TILE:min((ty + 1) * TILE, H)]
         mine[k * TILE:k * TILE + rows.shape[0]] = rows
