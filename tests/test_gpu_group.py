@@ -128,3 +128,41 @@ def test_group_nccl_single_process(g, ctx):
     grp = GaussianSplatGroup.create(asset, list(range(n)))
     _check_group(g, grp, cams, want)
     grp.close()
+
+
+def test_large_asset_bitmap_path(g, ctx, tmp_path):
+    """Above ~33 M splats the walkers' flag bitmaps no longer fit beside their static shared memory and are read through L1
+    instead (found by tools/big_scene.py at 50 M).  GS_WALK_BITS_GLOBAL=1 forces that path on a small scene: single GPU and an
+    emulated group of 3 must give the same order and pixels as the default path."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    script = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import unitygaussiansplatting_b200 as g\n"
+        "from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup\n"
+        "from util import camera\n"
+        "asset = g.synthetic_asset(g.SCENE_CLUSTERED, 120000, 0x5EED0075, 'Medium')\n"
+        "r = g.GaussianSplatRenderer(asset, g.GaussianSplatContext(0))\n"
+        "grp = GaussianSplatGroup.create(asset, [0, 0, 0], emulate=True)\n"
+        "out = {}\n"
+        "for k in range(3):\n"
+        "    cam = camera(g, 480, 300, pos=(0.3 * k, 0.5, -6.0 + 0.2 * k))\n"
+        "    rt = np.zeros((300, 480, 4), np.float16)\n"
+        "    r.SortAndRenderSplats(cam, rt=rt)\n"
+        "    rts = [np.zeros_like(rt) for _ in range(3)]\n"
+        "    grp.SortAndRenderSplats(cam, rts=rts)\n"
+        "    assert all(np.array_equal(x, rt) for x in rts) and np.array_equal(grp.readback_order(1), r.readback_order())\n"
+        "    out['rt%%d' %% k], out['order%%d' %% k] = rt, r.readback_order()\n"
+        "np.savez(sys.argv[1], **out)\n" % (str(root), str(root / "tests")))
+    res = {}
+    for flag in ("0", "1"):
+        path = tmp_path / ("walk%s.npz" % flag)
+        subprocess.run([sys.executable, "-c", script, str(path)], check=True, env=dict(os.environ, GS_WALK_BITS_GLOBAL=flag), timeout=300)
+        res[flag] = np.load(path)
+    for k in res["0"].files:
+        assert res["0"][k].any()
+        assert np.array_equal(res["0"][k], res["1"][k]), k

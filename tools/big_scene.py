@@ -33,3 +33,27 @@ keys = O.calc_distances(asset, fp, order, T)
 O.sort_pairs(keys, order, T)
 assert np.array_equal(r.readback_order(), order) and np.array_equal(r.readback_keys(), keys)
 print("order/keys bit-exact vs oracle at N =", n, "; alpha mean", float(rt[..., 3].float().mean()))
+
+# ---- the same scene through an emulated group (configs[4]: "8 x B200 splat-sharded sort + tile composite"): G contexts on this
+# GPU, device copies as exchange -- every kernel and all host logic of the group path at 50 M splats.  usage: big_scene.py N G
+G = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+if G:
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    want_order = r.readback_order()
+    want_rt = rt.clone()
+    r.Dispose()
+    del r
+    torch.cuda.empty_cache()
+    grp = GaussianSplatGroup.create(asset, [0] * G, emulate=True)
+    out = torch.zeros_like(rt)
+    cams = [cam] * 4          # the single-GPU renderer above rendered this camera 13 times from the identity order: ties are settled
+    for c in cams:
+        grp.SortAndRenderSplats(c, rts=[out] + [None] * (G - 1))
+    grp.sync()
+    st = grp.stats()
+    print("group of %d (emulated): slabs %s rows %s" % (G, list(st.slab_counts[:G]), list(st.row_bounds[:G + 1])), flush=True)
+    for i in range(G):
+        assert np.array_equal(grp.readback_order(i), want_order), "member %d: order differs" % i
+    assert torch.equal(out.view(torch.int16), want_rt.view(torch.int16)), "render target differs"
+    print("group of %d: order of every member and the render target bit-exact vs one GPU at N = %d" % (G, n))
+    grp.close()

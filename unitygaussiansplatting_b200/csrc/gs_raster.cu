@@ -207,7 +207,11 @@ BinScratch launch_binning(const FrameConsts &fc, const GsRenderOptions &opt, uin
   if (launches) *launches = 2 + passes;   // bin_emit, look-back clear, sort passes
   cudaMemsetAsync(sc.ghist, 0, 4 * 256 * sizeof(uint32_t), s);
   uint32_t words = (uint32_t)block_bits_words(n);
-  if (words * 4u > 32u * 1024u) words = 0;   // a bitmap that does not fit the default shared memory is read through L1 instead
+  static int bits_global = -1;   // GS_WALK_BITS_GLOBAL=1 forces the large-asset path (bitmap read through L1) for tests
+  if (bits_global < 0) { const char *e = getenv("GS_WALK_BITS_GLOBAL"); bits_global = (e && e[0] == '1') ? 1 : 0; }
+  if (bits_global) words = 0;
+  if (words * 4u > 16u * 1024u) words = 0;   // beside the kernel's 28 KB of static shared memory only 20 KB of the default 48 remain:
+                                              // a larger bitmap (> 33 M splats) is read through L1 instead
   k_bin_emit<<<nblocks, 256, words * 4u, s>>>(order, rect, block_bits, words, n, part, fc.binsX, bs.block_sums + 1, bs.block_sums, bs.capacity,
                                      bs.tile_keys, bs.tile_vals, bs.entry_count, sc.ghist, (uint32_t)bits, passes == 2);
   // the entry count lives on the device: a persistent grid sorts whatever it is (no capacity-sized grid or memset)

@@ -403,6 +403,9 @@ void launch_compact_order(const uint32_t *order, uint32_t n, const uint32_t *mas
   const uint32_t nblocks = (n + kCmpBlock - 1) / kCmpBlock;
   cudaMemsetAsync(status, 0, ((size_t)nblocks + 1) * sizeof(uint32_t), s);   // [0] ticket, [1..] look-back status
   uint32_t words = (uint32_t)group_bits_words(n);
+  static int bits_global = -1;   // GS_WALK_BITS_GLOBAL=1 forces the large-asset path (bitmap read through L1) for tests
+  if (bits_global < 0) { const char *e = getenv("GS_WALK_BITS_GLOBAL"); bits_global = (e && e[0] == '1') ? 1 : 0; }
+  if (bits_global) words = 0;
   if (words * 4u > 40u * 1024u) words = 0;   // a bitmap that does not fit the default shared memory is read through L1 instead
   k_compact_order<<<nblocks, 256, words * 4u, s>>>(order, n, mask, group_bits, words, key_table, out_ids, out_keys, status + 1, status, count_out);
 }
