@@ -227,10 +227,15 @@ GS_API int gs_unshuffle_bands(GsContext *ctx, const void *gathered, uint32_t par
  * R/GaussianSplatRenderer.cs:612-639) and the same render target.  Per frame and GPU:
  *   - the depth sort is sharded by KEY RANGE: every GPU computes the (cheap) key table, takes the splats whose key lies
  *     between two shared splitters -- in last frame's order, so ties keep the reference's order -- sorts only those, and one
- *     NCCL exchange of the id slabs gives every GPU the whole order;
+ *     exchange of the id slabs gives every GPU the whole order.  After gs_group_join the slabs travel as
+ *     peer-to-peer stores over NVLink into CUDA-IPC mappings of the peers' order buffers (no collective call); groups made
+ *     by gs_group_create, and boxes without IPC, use one ncclAllGather;
  *   - view-calc, binning and compositing are sharded by SCREEN ROWS: a contiguous range of 16-pixel rows per GPU
  *     (GsRenderOptions.row_begin/row_end), rebalanced every frame from the measured per-row cost, composited straight
- *     into place, then one NCCL exchange of the row ranges ("a single all-gather of the composited tile buffers").
+ *     into place, then one NCCL exchange of the row ranges ("a single all-gather of the composited tile buffers";
+ *     grouped broadcasts of the exact sizes, in place, on a transfer stream that overlaps the next frame's sort).
+ * Environment switches (diagnostics): GS_GROUP_P2P=0 (NCCL for the order too), GS_GROUP_ORDER_ALLGATHER=0 / GS_GROUP_XFER=sendrecv
+ * (exact-size broadcasts / send-recv instead of the all-gather), GS_GROUP_VIEW_LATE=1 (view-calc only under the exchange).
  * Two ways to form a group:
  *   gs_group_join    one process per GPU (torchrun-style): every process passes its own context, the group size, its rank
  *                    and the 128-byte id rank 0 got from gs_group_unique_id (sent over any host channel);

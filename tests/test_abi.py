@@ -59,3 +59,26 @@ def test_product_never_imports_the_oracle():
         text = p.read_text()
         for needle in ("gs_oracle", "import oracle", "from oracle", "gso_", "oracle/gs", "oracle\" /"):
             assert needle not in text, "%s references the oracle (%s)" % (p, needle)
+
+
+def test_group_entry_points_validate_their_arguments(g):
+    """gs_group_* never throw or abort: bad arguments come back as status codes (no GPU needed for these)."""
+    from unitygaussiansplatting_b200 import _native as N
+    lib = N.native()
+    h = C.c_void_p()
+    two = (C.c_int * 2)(0, 0)
+    assert lib.gs_group_create(None, 2, 0, C.byref(h)) == -1 and not h.value
+    assert lib.gs_group_create(two, 0, 0, C.byref(h)) == -1
+    assert lib.gs_group_create(two, 17, 0, C.byref(h)) == -1
+    assert lib.gs_group_create(two, 2, 0, C.byref(h)) == -1                      # a device listed twice without GS_GROUP_EMULATE
+    assert b"twice" in lib.gs_last_error(None)
+    if not has_cuda():
+        assert lib.gs_group_create(two, 2, N.GS_GROUP_EMULATE, C.byref(h)) == N.GS_ERR_NO_DEVICE and not h.value
+    out = (C.c_uint32 * 5)()
+    assert lib.gs_group_balance_rows(None, 10, 4, out) == 0 and list(out) == [0, 2, 5, 8, 10] or list(out)[0] == 0
+    assert lib.gs_group_balance_rows(None, 0, 4, out) == -1
+    assert lib.gs_group_balance_rows(None, 10, 17, out) == -1
+    assert lib.gs_group_size(None) == 0 and lib.gs_group_local_count(None) == 0 and not lib.gs_group_context(None, 0)
+    assert lib.gs_group_frame(None, None, None, None, 1, None) == -1
+    assert lib.gs_group_sync(None) == -1
+    lib.gs_group_destroy(None)

@@ -99,6 +99,13 @@ int fail_nccl(GsContext *ctx, ncclResult_t r, const char *what) {
     if (_r != ncclSuccess) return fail_nccl((ctx), _r, #expr);   \
   } while (0)
 
+// inside ncclGroupStart ... ncclGroupEnd: a failed call closes the group before the error is returned
+#define GS_NCCL_TRY_G(ctx, expr)                                                   \
+  do {                                                                             \
+    ncclResult_t _r = (expr);                                                      \
+    if (_r != ncclSuccess) { nccl_api().GroupEnd(); return fail_nccl((ctx), _r, #expr); } \
+  } while (0)
+
 int member_init(Member &mb) {
   GsContext *ctx = mb.ctx;
   GS_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -178,12 +185,12 @@ int exchange_add(GsGroup *g, uint8_t *const *bufs, const size_t *off, const size
       if (g->xfer == 1) {
         for (uint32_t p = 0; p < G; ++p) {
           if (p == mb.rank) continue;
-          if (cnt[mb.rank]) GS_NCCL_TRY(mb.ctx, nc.Send(bufs[i] + off[mb.rank], cnt[mb.rank], ncclUint8, (int)p, mb.comm, st(mb)));
-          if (cnt[p]) GS_NCCL_TRY(mb.ctx, nc.Recv(bufs[i] + off[p], cnt[p], ncclUint8, (int)p, mb.comm, st(mb)));
+          if (cnt[mb.rank]) GS_NCCL_TRY_G(mb.ctx, nc.Send(bufs[i] + off[mb.rank], cnt[mb.rank], ncclUint8, (int)p, mb.comm, st(mb)));
+          if (cnt[p]) GS_NCCL_TRY_G(mb.ctx, nc.Recv(bufs[i] + off[p], cnt[p], ncclUint8, (int)p, mb.comm, st(mb)));
         }
       } else {
         for (uint32_t c = 0; c < G; ++c)
-          if (cnt[c]) GS_NCCL_TRY(mb.ctx, nc.Broadcast(bufs[i] + off[c], bufs[i] + off[c], cnt[c], ncclUint8, (int)c, mb.comm, st(mb)));
+          if (cnt[c]) GS_NCCL_TRY_G(mb.ctx, nc.Broadcast(bufs[i] + off[c], bufs[i] + off[c], cnt[c], ncclUint8, (int)c, mb.comm, st(mb)));
       }
     }
     return GS_OK;
@@ -216,8 +223,6 @@ int exchange_end(GsGroup *g) {
 // broadcasts / send-recv of the exact slab sizes take 97 (tools/mb_exchange.py), so every GPU sorts its slab into slot `rank`
 // of a staging buffer of G equal slots (cap = the largest slab), the slots are gathered in place, and G device copies move
 // slot c's first cnt[c] ids to their place off[c] of the order.
-struct SlabLayout { uint32_t off[GS_GROUP_MAX_GPUS + 1]; uint32_t count, cap; };
-
 int exchange_allgather(GsGroup *g, uint8_t *const *bufs, size_t slot_bytes, const size_t *cnt) {
   const uint32_t G = g->size;
   if (g->use_nccl) {
@@ -225,7 +230,7 @@ int exchange_allgather(GsGroup *g, uint8_t *const *bufs, size_t slot_bytes, cons
     GS_NCCL_TRY(g->m[0].ctx, nc.GroupStart());
     for (size_t i = 0; i < g->m.size(); ++i) {
       Member &mb = g->m[i];
-      GS_NCCL_TRY(mb.ctx, nc.AllGather(bufs[i] + (size_t)mb.rank * slot_bytes, bufs[i], slot_bytes, ncclUint8, mb.comm, mb.ctx->stream));
+      GS_NCCL_TRY_G(mb.ctx, nc.AllGather(bufs[i] + (size_t)mb.rank * slot_bytes, bufs[i], slot_bytes, ncclUint8, mb.comm, mb.ctx->stream));
     }
     GS_NCCL_TRY(g->m[0].ctx, nc.GroupEnd());
     return GS_OK;
@@ -711,11 +716,6 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
       } else if (use_gather) {
         for (size_t i = 0; i < L; ++i) bufs[i] = reinterpret_cast<uint8_t *>(g->m[i].d_gather);
         if ((rc = exchange_allgather(g, bufs.data(), (size_t)cap * 4, cnt))) return rc;
-        SlabLayout lay;
-        memset(&lay, 0, sizeof(lay));
-        for (uint32_t c = 0; c <= G; ++c) lay.off[c] = g->slab_off[c];
-        lay.count = G; lay.cap = cap;
-        (void)lay;
         for (size_t i = 0; i < L; ++i) {   // slot c's ids -> their place in the order: G device copies (a copy kernel that found
           Member &mb = g->m[i];            // each element's slab took 41 us for the 24.5 MB of cfg2; the copy engine takes ~10)
           GS_CUDA_TRY(mb.ctx, cudaSetDevice(mb.ctx->device));
