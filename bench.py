@@ -472,9 +472,15 @@ def main():
             bounds = list(st.row_bounds[: world + 1])
             slabs = list(st.slab_counts[:world])
 
-        # e2e: rank 0 hands in a pinned host image (the display GPU's read-back); the others keep the frame on the device
+        # e2e: rank 0 hands in pinned host images (the display GPU's read-back), two in rotation, filled asynchronously: frame
+        # k's copy overlaps frame k+1's kernels and all copies have landed before the clock stops; the other ranks keep the
+        # frame on the device.  (GS_BENCH_SYNC_E2E=1: one image, every frame blocks until it has landed.)
         pinned = torch.empty((H, W, 4), dtype=torch.float16, pin_memory=True)
-        host_rt = pinned.numpy()
+        pinned2 = torch.empty((H, W, 4), dtype=torch.float16, pin_memory=True)
+        host_rts = (pinned.numpy(), pinned2.numpy())
+        async_e2e = (not args.baseline_partition) and os.environ.get("GS_BENCH_SYNC_E2E", "0") != "1"
+        if async_e2e and rank == 0:
+            grp.async_readback = True
 
         def step_e2e(k):
             if args.baseline_partition:
@@ -483,13 +489,17 @@ def main():
                     pinned.copy_(rt_dev, non_blocking=True)
                 stream.synchronize()
             else:
-                step_device(k, host_rt if rank == 0 else rt_dev)   # host image: D2H + sync inside gs_group_frame
+                step_device(k, host_rts[k & 1 if async_e2e else 0] if rank == 0 else rt_dev)   # host image: D2H enqueued (or awaited) inside gs_group_frame
         for k in range(args.warmup):
             step_e2e(k)
+        if not args.baseline_partition:
+            grp.sync()
         barrier()
         t0 = time.perf_counter()
         for k in range(args.warmup, total):
             step_e2e(k)
+        if not args.baseline_partition:
+            grp.sync()                       # every read-back has landed
         torch.cuda.synchronize()
         tt = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

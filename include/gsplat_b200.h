@@ -266,7 +266,8 @@ GS_API GsContext *gs_group_context(GsGroup *group, uint32_t local_index);
 GS_API int gs_group_asset_upload(GsGroup *group, const GsAssetDesc *desc, GsAsset **assets_out);
 /* SortAndRenderSplats (R/GaussianSplatRenderer.cs:108-169) on the group.  assets[i] / rts[i] belong to local member i;
  * rts[i] is a full-size image (device or host memory; NULL = this member keeps the frame in library scratch only).  Every
- * non-NULL rts[i] ends up holding the COMPLETE render target.  `opt`: blend_mode only.  Collective: every process of the
+ * non-NULL rts[i] ends up holding the COMPLETE render target.  `opt`: blend_mode, and GS_FLAG_ASYNC_READBACK for host images
+ * (the call returns with the read-back enqueued; gs_group_sync completes it).  Collective: every process of the
  * group must call it with the same parameters. */
 GS_API int gs_group_frame(GsGroup *group, GsAsset *const *assets, const GsFrameParams *fp, const GsRenderOptions *opt, int do_sort,
                           GsImage *const *rts);

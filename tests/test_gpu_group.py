@@ -166,3 +166,28 @@ def test_large_asset_bitmap_path(g, ctx, tmp_path):
     for k in res["0"].files:
         assert res["0"][k].any()
         assert np.array_equal(res["0"][k], res["1"][k]), k
+
+
+def test_group_async_host_readback(g, ctx):
+    """GS_FLAG_ASYNC_READBACK on the group path: host images are filled by the transfer stream after the call has returned;
+    gs_group_sync completes them.  Two pinned images per member in rotation, three frames in flight before the first sync."""
+    import torch
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 90000, 0x5EED0076, "Medium")
+    cams = _cams(g, 512, 320, 4)
+    want = _single_gpu_sequence(g, ctx, asset, cams)
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    grp = GaussianSplatGroup.create(asset, [0, 0, 0], emulate=True)
+    grp.async_readback = True
+    pins = [[torch.zeros((320, 512, 4), dtype=torch.float16).pin_memory() for _ in range(2)] for _ in range(3)]
+    for k, cam in enumerate(cams):
+        if k >= 2:                       # the images about to be reused hold frame k-2: complete and check them first
+            grp.sync()
+            for i in range(3):
+                assert np.array_equal(pins[i][k & 1].numpy().view(np.uint16), want[k - 2][1].view(np.uint16)), "frame %d member %d" % (k - 2, i)
+        grp.SortAndRenderSplats(cam, rts=[pins[i][k & 1].numpy() for i in range(3)])
+    grp.sync()
+    for k in (2, 3):
+        for i in range(3):
+            assert np.array_equal(pins[i][k & 1].numpy().view(np.uint16), want[k][1].view(np.uint16)), "frame %d member %d" % (k, i)
+    assert np.array_equal(grp.readback_order(2), want[3][0])
+    grp.close()

@@ -822,7 +822,12 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
   }
   g->frame++;
   g->hist_frames++;
-  if (host_out) return gs_group_sync(g);
+  // host images: filled by the transfer stream.  By default the call blocks until they are (like gs_frame); with
+  // GS_FLAG_ASYNC_READBACK it returns now and gs_group_sync completes them -- the images must be pinned and must not be
+  // reused before that (alternate two).  The next frame's compositor waits for this frame's copy before it touches the
+  // device image, so no second device image is needed.
+  const bool async_rb = opt_in && (opt_in->flags & GS_FLAG_ASYNC_READBACK) != 0;
+  if (host_out && !async_rb) return gs_group_sync(g);
   return GS_OK;
 }
 

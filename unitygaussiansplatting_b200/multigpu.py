@@ -146,6 +146,7 @@ class GaussianSplatGroup:
         self.localToWorldMatrix = None
         self.m_Cutouts, self.m_DeletedBits, self.m_SelectedBits = [], None, None
         self.blend_mode = N.GS_BLEND_FP16_ROP
+        self.async_readback = False  # host images are filled asynchronously (pinned memory; sync() completes them)
         self._keep = None
 
     @classmethod
@@ -186,6 +187,7 @@ class GaussianSplatGroup:
             fp = self.frame_params(cam)
         opt = N.GsRenderOptions()
         opt.blend_mode = self.blend_mode
+        opt.flags = N.GS_FLAG_ASYNC_READBACK if self.async_readback else 0
         ptrs = (C.POINTER(N.GsImage) * self.local_count)()
         ims = []
         if rts is not None:
