@@ -98,6 +98,15 @@ typedef struct GsFrameParams {
   const uint32_t *selected_bits;  /* host pointer, ceil(N/32) words or NULL: the edit selection (_SplatSelectedBits, :496).  A
                                      selected splat is drawn by the pixel shader's "selected" branch: magenta outline + tint,
                                      opacity from the gaussian alone (S/RenderGaussianSplats.shader:63-73,87-101) */
+  const float *scene_depth;       /* optional: the camera's depth buffer the splat pass tests against.  The reference binds the
+                                     current depth target beside _GaussianSplatRT (R/GaussianSplatRenderer.cs:195) and keeps
+                                     ShaderLab's default ZTest LEqual with ZWrite Off (S/RenderGaussianSplats.shader:8-12), so
+                                     splats behind opaque scene geometry are not drawn.  screen_w x screen_h float32, rows
+                                     tightly packed, in mat_proj_gpu's convention (reversed Z: 1 = near plane), where LEqual is
+                                     evaluated as "fragment depth >= stored depth"; every fragment of a splat has the depth
+                                     clip.z / clip.w of its centre (the quad is flat).  NULL = no depth test. */
+  uint32_t scene_depth_on_device; /* 0: scene_depth is host memory (uploaded per frame), 1: device memory (used in place) */
+  uint32_t reserved1;
 } GsFrameParams;
 
 typedef enum GsPixelFormat {

@@ -560,6 +560,7 @@ static inline int band_of_row(int32_t y, int bands, uint32_t H) {
 
 typedef struct DrawRec { /* per-splat constants of the draw, computed once (phase 1) */
   float cx, cy, i1x, i1y, i2x, i2y, cr, cg, cb, ca;
+  float z;                /* depth of every fragment of the (flat) quad: clip.z / clip.w */
   int32_t x0, x1, y0, y1; /* pixel rectangle to visit; x0 >= x1 marks "nothing to draw" */
 } DrawRec;
 
@@ -570,6 +571,11 @@ void gso_render(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t
 
 void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t W, uint32_t H, uint32_t blend_mode,
                     float *rt, int threads, const uint32_t *selected_bits) {
+  gso_render_ex(view, order, n, W, H, blend_mode, rt, threads, selected_bits, NULL);
+}
+
+void gso_render_ex(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t W, uint32_t H, uint32_t blend_mode,
+                   float *rt, int threads, const uint32_t *selected_bits, const float *scene_depth) {
   memset(rt, 0, (size_t)W * H * 16); /* ClearRenderTarget(0,0,0,0), R/GaussianSplatRenderer.cs:196 */
   if (threads < 1) threads = 1;
   const float fW = (float)W, fH = (float)H;
@@ -601,6 +607,7 @@ void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint
     r->cx = cx; r->cy = cy;
     r->i1x = a1x / n1; r->i1y = a1y / n1; r->i2x = a2x / n2; r->i2y = a2y / n2;
     r->cr = cr; r->cg = cg; r->cb = cb; r->ca = ca;
+    r->z = v->pos[2] / v->pos[3];
     r->x0 = x0; r->x1 = x1; r->y0 = y0; r->y1 = y1;
   }
   /* phase 2: rasterise + blend.  The image is cut into bands of rows; every band visits, in draw order, the records whose
@@ -659,6 +666,7 @@ void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint
             pr = lerpf(pr, 1.0f, 0.5f); pg = lerpf(pg, 0.0f, 0.5f); pb = lerpf(pb, 1.0f, 0.5f);
           }
           if (alpha < 0.003921569f) continue;       /* discard, :103-104 */
+          if (scene_depth && !(r->z >= scene_depth[(size_t)py * W + px])) continue; /* ZTest LEqual under reversed Z */
           float *d = &rt[((size_t)py * W + px) * 4];
           float om = 1.0f - d[3];                   /* Blend OneMinusDstAlpha One, :11 */
           float r0 = fmaf(pr * alpha, om, d[0]), r1 = fmaf(pg * alpha, om, d[1]), r2 = fmaf(pb * alpha, om, d[2]),

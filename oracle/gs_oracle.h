@@ -65,6 +65,8 @@ typedef struct GsoFrame {            /* same fields as GsFrameParams (include/gs
   const GsoCutout *cutouts;
   const uint32_t *deleted_bits;
   const uint32_t *selected_bits;     /* _SplatSelectedBits: read by the splat VERTEX shader, S/RenderGaussianSplats.shader:63-73 */
+  const float *scene_depth;          /* the camera's depth buffer the splat pass tests against (ZTest LEqual, ZWrite Off), W x H, reversed Z */
+  uint32_t scene_depth_on_device, reserved1;
 } GsoFrame;
 
 typedef struct GsoSplat {            /* SplatData, S/GaussianSplatting.hlsl:209-216 */
@@ -121,6 +123,12 @@ GSO_API void gso_render(const GsoView *view, const uint32_t *order, uint32_t n, 
  * the pixel shader's "selected" branch (:87-101).  selected_bits NULL == _SplatBitsValid 0 == gso_render. */
 GSO_API void gso_render_sel(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t width, uint32_t height,
                         uint32_t blend_mode, float *rt, int threads, const uint32_t *selected_bits);
+/* ... and with the scene's depth buffer bound (R/GaussianSplatRenderer.cs:195 binds the current depth target; the pass keeps
+ * ShaderLab's default ZTest LEqual, ZWrite Off, S/RenderGaussianSplats.shader:8-12).  A splat's quad is flat: every fragment
+ * has the depth clip.z / clip.w of the centre.  `scene_depth` is W x H float32 in the GPU projection's convention (reversed Z:
+ * 1 = near), under which LEqual is evaluated as "fragment depth >= stored depth".  NULL = no test. */
+GSO_API void gso_render_ex(const GsoView *view, const uint32_t *order, uint32_t n, uint32_t width, uint32_t height,
+                        uint32_t blend_mode, float *rt, int threads, const uint32_t *selected_bits, const float *scene_depth);
 
 /* ---- GaussianComposite.shader:35-39, Blend SrcAlpha OneMinusSrcAlpha (:11).
  *      target: W*H*4 floats, read-modify-write; target_fp16 != 0 rounds the result to half. ---- */

@@ -32,7 +32,7 @@ class GsoFrame(C.Structure):
                 ("mat_proj_gpu", C.c_float * 16), ("screen_w", C.c_float), ("screen_h", C.c_float), ("cam_pos_world", C.c_float * 3),
                 ("splat_scale", C.c_float), ("opacity_scale", C.c_float), ("sh_order", C.c_uint32), ("sh_only", C.c_uint32),
                 ("cutout_count", C.c_uint32), ("reserved0", C.c_uint32), ("cutouts", C.c_void_p), ("deleted_bits", C.c_void_p),
-                ("selected_bits", C.c_void_p)]
+                ("selected_bits", C.c_void_p), ("scene_depth", C.c_void_p), ("scene_depth_on_device", C.c_uint32), ("reserved1", C.c_uint32)]
 
 
 class GsoSplat(C.Structure):
@@ -67,6 +67,8 @@ def lib():
         L.gso_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
         L.gso_render_sel.restype = None
         L.gso_render_sel.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]
+        L.gso_render_ex.restype = None
+        L.gso_render_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gso_composite.restype, L.gso_composite.argtypes = None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
         L.gso_max_threads.restype, L.gso_max_threads.argtypes = C.c_int, []
         L.gso_export_data.restype, L.gso_export_data.argtypes = None, [C.POINTER(GsoAsset), C.POINTER(GsoFrame), C.c_void_p, C.c_int]
@@ -151,11 +153,17 @@ def export_data(asset, fp=None, threads: int = 1) -> np.ndarray:
 
 
 def render(view: np.ndarray, order: np.ndarray, width: int, height: int, blend_mode: int = 0, threads: int = 1,
-           selected_bits=None) -> np.ndarray:
+           selected_bits=None, scene_depth=None) -> np.ndarray:
     view = np.ascontiguousarray(view, np.uint32)
     order = np.ascontiguousarray(order, np.uint32)
     rt = np.zeros((height, width, 4), np.float32)
-    if selected_bits is None:
+    if scene_depth is not None:
+        depth = np.ascontiguousarray(scene_depth, np.float32)
+        assert depth.shape == (height, width)
+        bits = None if selected_bits is None else np.ascontiguousarray(selected_bits, np.uint32)
+        lib().gso_render_ex(view.ctypes.data, order.ctypes.data, order.size, width, height, blend_mode, rt.ctypes.data, threads,
+                            bits.ctypes.data if bits is not None else None, depth.ctypes.data)
+    elif selected_bits is None:
         lib().gso_render(view.ctypes.data, order.ctypes.data, order.size, width, height, blend_mode, rt.ctypes.data, threads)
     else:
         bits = np.ascontiguousarray(selected_bits, np.uint32)
@@ -181,7 +189,11 @@ def frame(asset, fp, prev_order=None, width=None, height=None, blend_mode: int =
     W, H = int(width or fp.screen_w), int(height or fp.screen_h)
     sel = C.cast(fp.selected_bits, C.POINTER(C.c_uint32)) if getattr(fp, "selected_bits", None) else None
     bits = np.ctypeslib.as_array(sel, shape=((n + 31) // 32,)) if sel else None
-    rt = render(view, order, W, H, blend_mode, threads, bits)
+    depth = None
+    if getattr(fp, "scene_depth", None):
+        assert not fp.scene_depth_on_device, "the oracle reads host memory"
+        depth = np.ctypeslib.as_array(C.cast(fp.scene_depth, C.POINTER(C.c_float)), shape=(H, W))
+    rt = render(view, order, W, H, blend_mode, threads, bits, depth)
     return {"keys": keys, "order": order, "view": view, "rt": rt}
 
 

@@ -39,7 +39,7 @@ def test_struct_layouts_match_the_header():
     from unitygaussiansplatting_b200 import _native as N
     assert C.sizeof(N.GsCutout) == 68                      # R/GaussianCutout.cs:20-24
     assert C.sizeof(N.GsAssetDesc) == 4 * 5 + 4 + 8 * 5 + 8 * 5
-    assert C.sizeof(N.GsFrameParams) == 64 * 4 + 8 + 12 + 8 + 8 + 8 + 4 + 24
+    assert C.sizeof(N.GsFrameParams) == 64 * 4 + 8 + 12 + 8 + 8 + 8 + 4 + 24 + 16
     assert C.sizeof(N.GsImage) == 32
     assert C.sizeof(N.GsRenderOptions) == 32
     assert C.sizeof(N.GsGroupStats) == 8 * 4 + 8 + 17 * 4 + 16 * 4

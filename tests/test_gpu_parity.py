@@ -388,3 +388,52 @@ def test_orthographic_projection(g, O, ctx):
     N.check(ctx.handle, lib.gs_render(ctx.handle, r._asset, C.byref(fp), C.byref(opt), C.byref(im)))
     assert np.array_equal(rt2, rt)
     r.Dispose()
+
+
+def test_scene_depth_buffer(g, O, ctx):
+    """GsFrameParams.scene_depth: the pass's ZTest LEqual against the camera's depth buffer (S/RenderGaussianSplats.shader:8-12,
+    R/GaussianSplatRenderer.cs:195).  A wall at view distance 6 over the left 60 % of the screen hides what lies behind it; the fused
+    frame, the staged draw, a device-resident depth buffer and an emulated group of 3 all equal the oracle's picture."""
+    import torch
+    asset = g.synthetic_asset(g.SCENE_CLUSTERED, 40000, 0x5EED0095, "Medium")
+    n = asset.splatCount
+    cam = camera(g, 400, 300)
+    P = cam.gpuProjectionMatrix(True).astype(np.float64)
+    clip = P @ np.array([0.0, 0.0, -6.0, 1.0])                 # view space looks down -z
+    z_wall = np.float32(clip[2] / clip[3])
+    assert 0.0 < z_wall < 1.0
+    depth = np.zeros((300, 400), np.float32)
+    depth[:, :240] = z_wall
+    r = g.GaussianSplatRenderer(asset, ctx)
+    r.sceneDepth = depth
+    rt = np.zeros((300, 400, 4), np.float16)
+    r.SortAndRenderSplats(cam, rt=rt)
+    fp, _keep = g.make_frame_params(cam, splat_count=n, scene_depth=depth)
+    ref = O.frame(asset, fp, threads=O.max_threads())
+    free_fp, _k2 = g.make_frame_params(cam, splat_count=n)
+    free = O.frame(asset, free_fp, threads=O.max_threads())
+    assert np.array_equal(ref["rt"][:, 240:], free["rt"][:, 240:]) and not np.array_equal(ref["rt"][:, :240], free["rt"][:, :240])
+    assert np.array_equal(rt.astype(np.float32), ref["rt"])
+    assert np.array_equal(r.readback_order(), ref["order"])
+    r.CalcViewData(cam)                                         # staged: view data (with the quad depths), then the draw
+    assert np.array_equal(r.readback_view(), ref["view"])
+    rt2 = np.zeros_like(rt)
+    r.DrawSplats(cam, rt2)
+    assert np.array_equal(rt2, rt)
+    r.sceneDepth = torch.from_numpy(depth).cuda()               # device-resident depth buffer: used in place
+    rt3 = np.zeros_like(rt)
+    r.SortAndRenderSplats(cam, rt=rt3)
+    assert np.array_equal(rt3, rt)
+    r.sceneDepth = None                                         # and without one the wall is gone
+    rt4 = np.zeros_like(rt)
+    r.SortAndRenderSplats(cam, rt=rt4)
+    assert np.array_equal(rt4.astype(np.float32), free["rt"])
+    r.Dispose()
+    from unitygaussiansplatting_b200.multigpu import GaussianSplatGroup
+    grp = GaussianSplatGroup.create(asset, [0, 0, 0], emulate=True)
+    grp.sceneDepth = depth
+    rts = [np.zeros_like(rt) for _ in range(3)]
+    grp.SortAndRenderSplats(cam, rts=rts)
+    for i in range(3):
+        assert np.array_equal(rts[i], rt)
+    grp.close()

@@ -286,3 +286,27 @@ def test_sh_order3_matches_the_published_real_sh_basis(g, O):
             v, _ = _view(g, O, asset, cam, sh_order=order)
             got = np.array([v["r"][0], v["g"][0], v["b"][0]], np.float64)
             assert np.allclose(got, want, rtol=1.5e-3, atol=2e-4), (order, got, want)     # the result is stored as half
+
+
+def test_scene_depth_buffer_hides_what_lies_behind_it(g, O):
+    """The splat pass keeps ShaderLab's default ZTest LEqual against the camera's depth buffer (S/RenderGaussianSplats.shader:8-12,
+    depth target bound at R/GaussianSplatRenderer.cs:195).  Oracle semantics: every fragment of a splat has the depth
+    clip.z / clip.w of the centre; under the GPU projection's reversed Z it passes iff that depth >= the stored one."""
+    W, H = 96, 64
+    cam = camera(g, W, H, fov=50.0, pos=(0.0, 0.0, -3.0))
+    near = one_splat(g, pos=(-0.4, 0.0, 0.0), scale=(0.2, 0.2, 0.2), opacity=0.9, dc0=(0.9, 0.1, 0.1))
+    fp, _keep = g.make_frame_params(cam, sh_order=0)
+    view = O.calc_view(near, fp)
+    z = view.view(np.float32)[0, 2] / view.view(np.float32)[0, 3]        # the quad's depth, reversed Z: nearer = larger
+    assert 0.0 < z < 1.0
+    order = np.arange(1, dtype=np.uint32)
+    free = O.render(view, order, W, H, 1)
+    assert free[..., 3].max() > 0.5
+    for stored, visible in ((np.float32(z), True), (np.nextafter(np.float32(z), np.float32(2)), False), (np.float32(0.0), True), (np.float32(1.0), False)):
+        depth = np.full((H, W), stored, np.float32)
+        img = O.render(view, order, W, H, 1, scene_depth=depth)
+        assert np.array_equal(img, free) if visible else not img.any(), (stored, visible)
+    half = np.zeros((H, W), np.float32)
+    half[:, W // 2:] = 1.0                                                # an occluder over the right half of the screen only
+    img = O.render(view, order, W, H, 1, scene_depth=half)
+    assert np.array_equal(img[:, :W // 2], free[:, :W // 2]) and not img[:, W // 2:].any()

@@ -49,6 +49,7 @@ class GsFrameParams(C.Structure):
         ("sh_order", C.c_uint32), ("sh_only", C.c_uint32),
         ("cutout_count", C.c_uint32), ("reserved0", C.c_uint32),
         ("cutouts", C.c_void_p), ("deleted_bits", C.c_void_p), ("selected_bits", C.c_void_p),
+        ("scene_depth", C.c_void_p), ("scene_depth_on_device", C.c_uint32), ("reserved1", C.c_uint32),
     ]
 
 

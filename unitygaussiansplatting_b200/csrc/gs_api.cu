@@ -220,6 +220,25 @@ int upload_frame_inputs(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, cu
   return GS_OK;
 }
 
+// The scene depth buffer the splat pass is tested against (GsFrameParams.scene_depth): used in place when it is device
+// memory, uploaded on `stream` when it is host memory.
+int bind_depth(GsContext *ctx, const GsFrameParams *fp, cudaStream_t stream) {
+  ctx->cur_depth = nullptr;
+  if (!fp->scene_depth) return GS_OK;
+  if (fp->scene_depth_on_device) { ctx->cur_depth = fp->scene_depth; return GS_OK; }
+  const size_t bytes = (size_t)(uint32_t)fp->screen_w * (uint32_t)fp->screen_h * sizeof(float);
+  if (bytes > ctx->depth_bytes) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_depth);
+    ctx->d_depth = nullptr; ctx->depth_bytes = 0;
+    GS_CUDA_TRY(ctx, cudaMalloc(&ctx->d_depth, bytes));
+    ctx->depth_bytes = bytes;
+  }
+  GS_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_depth, fp->scene_depth, bytes, cudaMemcpyHostToDevice, stream));
+  ctx->cur_depth = ctx->d_depth;
+  return GS_OK;
+}
+
 int check_params(GsContext *ctx, GsAsset *as, const GsFrameParams *fp) {
   if (!ctx || !as || !fp) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "null context/asset/params");
   if (as->ctx != ctx) return fail(ctx, GS_ERR_INVALID_ARGUMENT, "asset belongs to another context");
@@ -260,7 +279,10 @@ int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameCon
   if (rc) return rc;
   const bool own = stream == ctx->stream;   // the group path runs view-calc beside the sort on a second stream and times it itself
   if (own) rec(ctx, EV_VIEW0);
-  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, ctx->d_selected, as->view, as->rect, as->draw, as->block_bits, cull, make_partition(opt), stream);
+  if (fp->scene_depth && !as->zndc) GS_CUDA_TRY(ctx, cudaMalloc(&as->zndc, (size_t)as->av.n * sizeof(float) + 16));
+  as->zndc_valid = fp->scene_depth != nullptr;
+  launch_calc_view(as->av, fc, ctx->d_cutouts, ctx->d_deleted, ctx->d_selected, as->view, as->rect, as->draw, as->block_bits,
+                   as->zndc_valid ? as->zndc : nullptr, cull, make_partition(opt), stream);
   if (own) rec(ctx, EV_VIEW1);
   ctx->launches += 1;
   as->view_valid = !cull;
@@ -302,7 +324,7 @@ int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const GsRender
   int bin_launches = 0;
   const BinScratch lists = launch_binning(fc, opt, as->av.n, as->order, as->rect, as->block_bits, ctx->bin, ctx->sort, ctx->stream, &bin_launches);
   rec(ctx, EV_BIN1);
-  launch_raster(fc, opt, as->draw, lists, d_rt, pitch, fmt, ctx->stream);
+  launch_raster(fc, opt, as->draw, lists, d_rt, pitch, fmt, ctx->stream, ctx->cur_depth ? as->zndc : nullptr, ctx->cur_depth);
   rec(ctx, EV_RASTER1);
   ctx->launches += bin_launches + 3;  // bin_emit, look-back clear, 1-2 sort passes; bin_ranges, tile_order, raster
   GS_CUDA_TRY(ctx, cudaGetLastError());
@@ -414,7 +436,7 @@ void gs_destroy(GsContext *ctx) {
   cudaFree(ctx->sort.alt_keys); cudaFree(ctx->sort.alt_vals); cudaFree(ctx->sort.lookback);
   cudaFree(ctx->sort.ghist); cudaFree(ctx->sort.tickets); cudaFree(ctx->d_scalar);
   cudaFree(ctx->bin.bin_ranges); cudaFree(ctx->bin.tile_cost); cudaFree(ctx->bin.tile_order); cudaFree(ctx->bin.block_sums); cudaFree(ctx->bin.entry_count); cudaFree(ctx->bin.tile_keys); cudaFree(ctx->bin.tile_vals);
-  cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted); cudaFree(ctx->d_selected);
+  cudaFree(ctx->rt_scratch); cudaFree(ctx->tgt_scratch); cudaFree(ctx->d_cutouts); cudaFree(ctx->d_deleted); cudaFree(ctx->d_selected); cudaFree(ctx->d_depth);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (int i = 0; i < 2; ++i) {
     cudaFree(ctx->rt_async[i]);
@@ -532,7 +554,7 @@ void gs_asset_destroy(GsAsset *as) {
   if (!as) return;
   if (as->ctx) { cudaSetDevice(as->ctx->device); cudaStreamSynchronize(as->ctx->stream); }
   cudaFree(as->d_pos); cudaFree(as->d_other); cudaFree(as->d_sh); cudaFree(as->d_color); cudaFree(as->d_chunks);
-  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->draw); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n); cudaFree(as->block_bits); cudaFree(as->slab_mask); cudaFree(as->order_tmp); cudaFree(as->order_alt); cudaFree(as->slab_group_bits);
+  cudaFree(as->order); cudaFree(as->keys); cudaFree(as->key_table); cudaFree(as->draw); cudaFree(as->view); cudaFree(as->rect); cudaFree(as->d_n); cudaFree(as->block_bits); cudaFree(as->zndc); cudaFree(as->slab_mask); cudaFree(as->order_tmp); cudaFree(as->order_alt); cudaFree(as->slab_group_bits);
   delete as;
 }
 
@@ -581,6 +603,8 @@ int gs_render(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRend
   const uint32_t H = opt.band_packed ? partition_own_bin_rows(opt, fc.binsY) * kBin : (uint32_t)fp->screen_h;
   if ((rc = image_ok(ctx, rt, W, H, &pitch))) return rc;
   for (int e = EV_BIN1; e < EV_COUNT; ++e) ctx->ev_valid[e] = false;
+  if ((rc = bind_depth(ctx, fp, ctx->stream))) return rc;
+  if (ctx->cur_depth && !as->zndc_valid) return fail(ctx, GS_ERR_NOT_READY, "a scene depth buffer needs the quad depths: run gs_calc_view with scene_depth set");
   rec(ctx, EV_VIEW1);
   if (rt->memory == GS_MEM_DEVICE) return do_render(ctx, as, fc, opt, rt->data, pitch, rt->format);
   const uint32_t tight = W * pix_bytes(rt->format);
@@ -666,6 +690,7 @@ int gs_frame(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const GsRende
     d_rt = ctx->rt_scratch;
     if ((rc = init_staging(ctx, opt, d_rt, d_pitch, W, H, rt_fmt, rt, rt_pitch))) return rc;
   }
+  if ((rc = bind_depth(ctx, fp, ctx->stream))) return rc;
   if ((rc = do_render(ctx, as, fc, opt, d_rt, d_pitch, rt_fmt))) return rc;
   bool synced = false;
   if (async_rb) {

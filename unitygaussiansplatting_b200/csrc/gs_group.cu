@@ -771,6 +771,7 @@ int gs_group_frame(GsGroup *g, GsAsset *const *assets, const GsFrameParams *fp, 
       if (mb.image_pending) GS_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, mb.ev_image, 0));
       if (timing) cudaEventRecord(mb.tev[GT_VIEWWAIT], ctx->stream);
       rec(ctx, EV_VIEW1);
+      if ((rc = bind_depth(ctx, fp, ctx->stream))) return rc;
       if ((rc = do_render(ctx, as, fc, opt, d_rt, pitch, fmt))) return rc;
       ctx->launches += 1;   // k_row_costs, launched on the transfer stream below
     } else if (timing) {

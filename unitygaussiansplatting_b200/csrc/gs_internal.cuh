@@ -61,6 +61,9 @@ struct GsContext {
   size_t deleted_words = 0;
   uint32_t *d_selected = nullptr;
   size_t selected_words = 0;
+  float *d_depth = nullptr;          // the frame's scene depth buffer when it was handed over in host memory
+  size_t depth_bytes = 0;
+  const float *cur_depth = nullptr;  // what the compositor tests against this frame (nullptr: no depth test)
   uint32_t launches = 0;
 };
 
@@ -72,6 +75,8 @@ struct GsAsset {
   uint32_t *block_bits = nullptr;  // bit j: some splat of block j (256 splats) got a bin rectangle from the last view-calc
   // group path only (allocated by gs_group_*): slab membership (bit per splat, byte per 128), compaction output / sort ping-pong payload
   uint32_t *slab_mask = nullptr, *order_tmp = nullptr;
+  float *zndc = nullptr;           // per-splat quad depth clip.z / clip.w, written by view-calc when a scene depth buffer is bound
+  bool zndc_valid = false;
   uint32_t *order_alt = nullptr;   // peer-to-peer order exchange: `order` and `order_alt` alternate as last / new draw order
   uint32_t *slab_group_bits = nullptr;
   float4 *draw = nullptr;  // raster-ready 48-byte records of the drawable splats
@@ -87,6 +92,7 @@ int check_params(GsContext *ctx, GsAsset *as, const GsFrameParams *fp);
 int check_options(GsContext *ctx, const FrameConsts &fc, GsRenderOptions &opt);
 int ensure_sort_scratch(GsContext *ctx, uint32_t capacity);
 int upload_frame_inputs(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, cudaStream_t stream);
+int bind_depth(GsContext *ctx, const GsFrameParams *fp, cudaStream_t stream);   // sets ctx->cur_depth for the draw that follows
 int do_view(GsContext *ctx, GsAsset *as, const GsFrameParams *fp, const FrameConsts &fc, bool cull, const GsRenderOptions &opt,
             cudaStream_t stream);
 int do_render(GsContext *ctx, GsAsset *as, const FrameConsts &fc, const GsRenderOptions &opt, void *d_rt, uint32_t pitch, uint32_t fmt);

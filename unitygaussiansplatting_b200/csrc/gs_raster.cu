@@ -246,6 +246,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -339,13 +343,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// SEL: an edit selection is bound; records with opacity -1 are selected splats and take the pixel shader's other branch
-// (S/RenderGaussianSplats.shader:87-101).  A separate instantiation, so that frames without a selection pay nothing.
+// SEL ("extras"): a separate instantiation for frames with an edit selection and / or a scene depth buffer bound, so that
+// ordinary frames pay nothing.  Selected splats (records with opacity -1) take the pixel shader's other branch
+// (S/RenderGaussianSplats.shader:87-101); with `scene_depth` every fragment is depth-tested like the pass's ZTest LEqual
+// (reversed Z: quad depth >= stored depth), the per-splat quad depths being staged beside the records.
 template <bool FP16_ROP, int OUT_FMT, bool STATS, bool TMA, bool SEL = false>
 __global__ void __launch_bounds__(256)
 k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const uint2 *__restrict__ bin_ranges,
          const uint32_t *__restrict__ tile_vals, const uint32_t *__restrict__ tile_order, uint32_t *__restrict__ tile_cost, uint32_t ntx,
-         uint8_t *__restrict__ rt, uint32_t pitch, uint32_t band_packed, uint32_t load_rt, unsigned long long *stats) {
+         uint8_t *__restrict__ rt, uint32_t pitch, uint32_t band_packed, uint32_t load_rt, unsigned long long *stats,
+         const float *__restrict__ zndc, const float *__restrict__ scene_depth) {
   uint32_t st_batches = 0, st_culls = 0, st_cand = 0, st_eval = 0, st_blend = 0;   // GS_RASTER_STATS diagnostics (per warp)
   unsigned long long st_t0 = 0;
   if (STATS) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(st_t0));
@@ -353,6 +360,8 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   // cp.async path: planar [buf][plane][entry]; TMA path: the 48-byte records as they are, [buf][entry][plane].
   __shared__ __align__(128) float4 s_rec[2][3][256];  // plane 0: cx, cy, i1x, i1y   1: i2x, i2y, opacity, hx   2: r, g, b, hy
   __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ float s_z[SEL ? 2 : 1][SEL ? 256 : 1];   // quad depths of the staged batch (depth test only)
+  const bool depth_test = SEL && scene_depth != nullptr;
   constexpr int ES = TMA ? 3 : 1;     // float4 stride between consecutive entries of one plane
   constexpr int PS = TMA ? 1 : 256;   // float4 stride between the planes of one entry
   if (TMA) {
@@ -384,6 +393,9 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
   const bool in_image = px < (uint32_t)fc.screenW && py < (uint32_t)fc.screenH;
 
   float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;  // ClearRenderTarget(0,0,0,0), R/GaussianSplatRenderer.cs:196
+  // the scene's depth at this pixel (depth target bound at R/GaussianSplatRenderer.cs:195; ZTest LEqual, ZWrite Off)
+  float zscene = 0.0f;
+  if (SEL && depth_test && in_image) zscene = __ldg(scene_depth + (size_t)py * (uint32_t)fc.screenW + px);
   // where this pixel lives in the target (band-packed: own bin row k of an interleaved partition -> rows [64k, 64k+64))
   const uint32_t out_row = band_packed ? part.own_rows_below(brow) * kBin + (py - brow * kBin) : py;
   if (load_rt && in_image) {
@@ -418,6 +430,7 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
       cp_async16(&s_rec[buf][0][tid], src);
       cp_async16(&s_rec[buf][1][tid], src + 1);
       cp_async16(&s_rec[buf][2][tid], src + 2);
+      if (SEL && depth_test) cp_async4(&s_z[SEL ? buf : 0][SEL ? tid : 0], zndc + id);
     }
     cp_async_commit();
   };
@@ -476,7 +489,9 @@ k_raster(FrameConsts fc, Partition part, const float4 *__restrict__ draw, const 
         } else {
           alpha = __saturatef(alpha * B.z);                               // :83-86 (saturate: NaN -> 0, one instruction)
         }
-        if (inside && alpha >= 0.003921569f) {                            // discard below 1/255 (:103-104)
+        bool pass = inside && alpha >= 0.003921569f;                      // discard below 1/255 (:103-104)
+        if (SEL && depth_test) pass = pass && (s_z[SEL ? buf : 0][SEL ? j : 0] >= zscene);   // ZTest LEqual, reversed Z
+        if (pass) {
           if (STATS) ++st_blend;
           float4 C = s_c[j * ES];
           if (SEL && tint) {
@@ -538,7 +553,7 @@ unsigned long long *g_raster_stats = nullptr;
 static constexpr int kRasterTmaDefault = 0;
 
 void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const float4 *draw, const BinScratch &bs, void *rt,
-                   uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s) {
+                   uint32_t rt_pitch_bytes, uint32_t rt_format, cudaStream_t s, const float *zndc, const float *scene_depth) {
   const Partition part = make_partition(opt);
   const uint32_t rows = part.own_tile_rows(fc.binsY);
   if (!rows || !fc.binsX) return;
@@ -562,10 +577,10 @@ void launch_raster(const FrameConsts &fc, const GsRenderOptions &opt, const floa
   k_bin_ranges<<<(bins + 7) / 8, 256, 0, s>>>(bs.tile_keys, bs.entry_count, bins, ranges);
 #define GS_LAUNCH_RASTER(ROP, FMT)                                                                                              \
   do {                                                                                                                         \
-    if (fc.selValid) k_raster<ROP, FMT, false, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
-    else if (tma) k_raster<ROP, FMT, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
-    else if (stats) k_raster<ROP, FMT, true, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
-    else k_raster<ROP, FMT, false, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats); \
+    if (fc.selValid || scene_depth) k_raster<ROP, FMT, false, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats, zndc, scene_depth); \
+    else if (tma) k_raster<ROP, FMT, false, true><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats, nullptr, nullptr); \
+    else if (stats) k_raster<ROP, FMT, true, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats, nullptr, nullptr); \
+    else k_raster<ROP, FMT, false, false><<<grid, 256, 0, s>>>(fc, part, draw, ranges, bs.tile_vals, bs.tile_order, bs.tile_cost, ntx, out, rt_pitch_bytes, packed, load, stats, nullptr, nullptr); \
   } while (0)
   if (rt_format == GS_PIX_RGBA16F) {
     if (rop) GS_LAUNCH_RASTER(true, GS_PIX_RGBA16F); else GS_LAUNCH_RASTER(false, GS_PIX_RGBA16F);

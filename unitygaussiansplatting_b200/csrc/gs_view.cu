@@ -294,7 +294,7 @@ template <int SHFMT, bool CULL, bool BC7>
 __global__ void __launch_bounds__(256, (CULL && SHFMT == 3 && !BC7) ? 5 : 1)
 k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, const uint32_t *__restrict__ deleted,
             const uint32_t *__restrict__ selected, uint32_t *__restrict__ view_out, uint32_t *__restrict__ rect_out, float4 *__restrict__ draw_out,
-            uint32_t *__restrict__ block_bits, Partition part) {
+            uint32_t *__restrict__ block_bits, float *__restrict__ zndc, Partition part) {
   __shared__ __align__(16) uint32_t s_view[256 * 10];
   __shared__ __align__(16) Chunk s_chunk;
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
@@ -618,6 +618,8 @@ k_calc_view(AssetView a, FrameConsts fc, const GsCutout *__restrict__ cutouts, c
           d[0] = make_float4(fp.cx, fp.cy, fp.i1x, fp.i1y);
           d[1] = make_float4(fp.i2x, fp.i2y, fp.ca, fp.hx);
           d[2] = make_float4(f16hi(vw[8]), f16lo(vw[8]), f16hi(vw[9]), fp.hy);
+          // depth of the (flat) quad's fragments, for the depth test against the scene's depth buffer when one is bound
+          if (zndc) zndc[idx] = __fdiv_rn(clip.z, clip.w);
         }
       }
       }  // reachable
@@ -671,13 +673,13 @@ void launch_calc_distances(const AssetView &a, const FrameConsts &fc, uint32_t *
 
 template <bool CULL>
 static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
-                               uint32_t *rect, float4 *draw, uint32_t *block_bits, const Partition &part, cudaStream_t s) {
+                               uint32_t *rect, float4 *draw, uint32_t *block_bits, float *zndc, const Partition &part, cudaStream_t s) {
   const uint32_t grid = (a.n + 255) / 256;
   // BC7 colour (VeryLow preset) is a separate instantiation: the block decode must not cost the other formats registers
 #define GS_VIEW(SH)                                                                                                        \
   do {                                                                                                                    \
-    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, part);  \
-    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, part);               \
+    if (a.colFmt == 3) k_calc_view<SH, CULL, true><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, zndc, part);  \
+    else k_calc_view<SH, CULL, false><<<grid, 256, 0, s>>>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, zndc, part);               \
   } while (0)
   switch (a.shFmt) {
     case 0: GS_VIEW(0); break;
@@ -690,11 +692,11 @@ static void launch_calc_view_t(const AssetView &a, const FrameConsts &fc, const 
 }
 
 void launch_calc_view(const AssetView &a, const FrameConsts &fc, const GsCutout *cutouts, const uint32_t *deleted, const uint32_t *selected, uint32_t *view,
-                      uint32_t *rect, float4 *draw, uint32_t *block_bits, bool cull_undrawable, const Partition &part, cudaStream_t s) {
+                      uint32_t *rect, float4 *draw, uint32_t *block_bits, float *zndc, bool cull_undrawable, const Partition &part, cudaStream_t s) {
   if (!a.n) return;
   cudaMemsetAsync(block_bits, 0, block_bits_words(a.n) * sizeof(uint32_t), s);
-  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, part, s);
-  else launch_calc_view_t<false>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, part, s);
+  if (cull_undrawable) launch_calc_view_t<true>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, zndc, part, s);
+  else launch_calc_view_t<false>(a, fc, cutouts, deleted, selected, view, rect, draw, block_bits, zndc, part, s);
 }
 
 }  // namespace gs

@@ -144,7 +144,7 @@ class GaussianSplatGroup:
         self.m_SplatScale, self.m_OpacityScale, self.m_SHOrder, self.m_SHOnly = 1.0, 1.0, 3, False
         self.m_SortNthFrame, self.m_FrameCounter = 1, 0
         self.localToWorldMatrix = None
-        self.m_Cutouts, self.m_DeletedBits, self.m_SelectedBits = [], None, None
+        self.m_Cutouts, self.m_DeletedBits, self.m_SelectedBits, self.sceneDepth = [], None, None, None
         self.blend_mode = N.GS_BLEND_FP16_ROP
         self.async_readback = False  # host images are filled asynchronously (pinned memory; sync() completes them)
         self._keep = None
@@ -175,7 +175,7 @@ class GaussianSplatGroup:
     def frame_params(self, cam):
         from .renderer import make_frame_params
         fp, self._keep = make_frame_params(cam, self.localToWorldMatrix, self.m_SplatScale, self.m_OpacityScale, self.m_SHOrder,
-                                           self.m_SHOnly, self.m_Cutouts, self.m_DeletedBits, self.splatCount, self.m_SelectedBits)
+                                           self.m_SHOnly, self.m_Cutouts, self.m_DeletedBits, self.splatCount, self.m_SelectedBits, self.sceneDepth)
         return fp
 
     def SortAndRenderSplats(self, cam, rts=None, fp=None):

@@ -174,7 +174,7 @@ def cutout_array(cutouts):
 
 
 def make_frame_params(cam: Camera, localToWorld=None, splat_scale=1.0, opacity_scale=1.0, sh_order=3, sh_only=False, cutouts=None,
-                      deleted_bits=None, splat_count=0, selected_bits=None):
+                      deleted_bits=None, splat_count=0, selected_bits=None, scene_depth=None):
     """The uniforms C# binds in CalcViewData / SortPoints (R/GaussianSplatRenderer.cs:586-606,617-631).
     Returns (GsFrameParams, keepalive list for the borrowed host pointers)."""
     fp = N.GsFrameParams()
@@ -204,6 +204,16 @@ def make_frame_params(cam: Camera, localToWorld=None, splat_scale=1.0, opacity_s
         assert bits.size >= (splat_count + 31) // 32
         fp.selected_bits = bits.ctypes.data
         keep.append(bits)
+    if scene_depth is not None:    # (H, W) float32: numpy host array or torch CUDA tensor
+        if isinstance(scene_depth, np.ndarray):
+            depth = np.ascontiguousarray(scene_depth, np.float32)
+            assert depth.shape == (cam.pixelHeight, cam.pixelWidth)
+            fp.scene_depth, fp.scene_depth_on_device = depth.ctypes.data, 0
+        else:
+            depth = scene_depth.contiguous()
+            assert tuple(depth.shape) == (cam.pixelHeight, cam.pixelWidth) and depth.element_size() == 4
+            fp.scene_depth, fp.scene_depth_on_device = depth.data_ptr(), 1 if depth.is_cuda else 0
+        keep.append(depth)
     return fp, keep
 
 
@@ -226,6 +236,7 @@ class GaussianSplatRenderer:
         self.m_Cutouts = []          # list of (4x4 matrix, type_and_flags)
         self.m_DeletedBits = None    # np.uint32[ceil(N/32)] or None
         self.m_SelectedBits = None   # np.uint32[ceil(N/32)] or None (m_GpuEditSelected, R/GaussianSplatRenderer.cs:496)
+        self.sceneDepth = None       # (H, W) float32 camera depth buffer (reversed Z) the splats are depth-tested against, or None
         self.blend_mode = N.GS_BLEND_FP16_ROP
         self.partition = (0, 0, 1)   # index, count, band_rows
         self.band_packed = False
@@ -260,7 +271,8 @@ class GaussianSplatRenderer:
     # -- uniforms ------------------------------------------------------------------------------
     def frame_params(self, cam: Camera) -> N.GsFrameParams:
         fp, self._keep = make_frame_params(cam, self.localToWorldMatrix, self.m_SplatScale, self.m_OpacityScale, self.m_SHOrder,
-                                           self.m_SHOnly, self.m_Cutouts, self.m_DeletedBits, self.splatCount, self.m_SelectedBits)
+                                           self.m_SHOnly, self.m_Cutouts, self.m_DeletedBits, self.splatCount, self.m_SelectedBits,
+                                           self.sceneDepth)
         return fp
 
     def _options(self) -> N.GsRenderOptions:
