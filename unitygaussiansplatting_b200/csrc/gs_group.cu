@@ -15,9 +15,13 @@
 //     re-cut every frame from the per-row cost measured two frames earlier (exchanged with the pixels), which is the
 //     same on every GPU, so the cuts agree without a negotiation either.
 // Streams: the sort chain and the compositing chain run on the context stream, view-calc beside the sort on a second
-// stream; the only host wait inside a frame is for the 128-byte slab table (the GPU is busy with view-calc meanwhile).
-// Exchanges are grouped NCCL broadcasts in place (an all-gather with per-rank sizes); in GS_GROUP_EMULATE, or without NCCL in
-// a single process, plain device-to-device copies ordered by events.
+// (lowest-priority) stream, the exchange of composited rows / row costs and the host read-back on a third, overlapping the
+// next frame; the only host wait inside a frame is for the 128-byte slab table (the GPU is busy with view-calc meanwhile).
+// Order exchange, fastest available first: one process per GPU -> remote stores into the peers' order buffers mapped through
+// CUDA IPC (k_push_slab / k_wait_slabs, no NCCL call in the frame); several members in one process, or IPC unavailable ->
+// one ncclAllGather of equal slots + G device copies; badly unbalanced slabs -> grouped NCCL broadcasts of the exact sizes in
+// place.  Row exchange: grouped NCCL broadcasts in place.  In GS_GROUP_EMULATE, or without NCCL in a single process, plain
+// device-to-device copies ordered by events stand in for every exchange.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
