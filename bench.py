@@ -17,10 +17,11 @@ roofline the radix-sort digit pass (k_onesweep), the kernel BASELINE.json's metr
          `traffic` and every `*_dram_gbs_physical` come from the committed ncu --set full summary named in "ncu_source".
 cpu_baseline / --impl reference: the CPU restatement of the reference's shaders (oracle/), all host cores -- the reference has
          no CPU implementation of this path and its C#/HLSL cannot run here, so kind = "port".
-N > 1    the group path (include/gsplat_b200.h gs_group_*): key-range-sharded depth sort + one NCCL exchange of the order
-         slabs, row-range-sharded view-calc / binning / compositing + one NCCL exchange of the composited rows, NCCL called
-         by the library itself.  Before the timed region EVERY rank renders the same frames on its own GPU alone and asserts
-         that the group's draw order and render target are bit-identical.
+N > 1    the group path (include/gsplat_b200.h gs_group_*): key-range-sharded depth sort + one exchange of the order slabs
+         (stores into the peers' order buffers over NVLink; NCCL all-gather if CUDA IPC is unavailable), row-range-sharded
+         view-calc / binning / compositing + one NCCL exchange of the composited rows, all of it issued by the library
+         itself.  Before the timed region EVERY rank renders the same frames on its own GPU alone and asserts that the
+         group's draw order and render target are bit-identical.
 """
 from __future__ import annotations
 
@@ -412,8 +413,8 @@ def main():
 
             def step_device(k, out=rt_dev):
                 grp.SortAndRenderSplats(cams[k], rts=[out], fp=fps[k])
-            parallelism = ("group x%d: key-range-sharded sort + NCCL order exchange, row-range-sharded view-calc/bin/composite + NCCL row "
-                           "exchange (gs_group_frame)" % world)
+            parallelism = ("group x%d: key-range-sharded sort + order exchange (NVLink peer stores, NCCL fallback), row-range-sharded "
+                           "view-calc/bin/composite + NCCL row exchange (gs_group_frame)" % world)
             # ---- the NCCL path against this GPU alone, outside the timed region: order and pixels bit-equal, 3 orbit frames ----
             ctx1 = g.GaussianSplatContext(local)
             r1 = g.GaussianSplatRenderer(asset, ctx1)

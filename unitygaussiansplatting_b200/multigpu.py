@@ -1,11 +1,14 @@
-"""Screen-tile partition across the GPUs of one box (the reference is single-GPU).
+"""Several GPUs of one box (the reference is single-GPU).
 
-Every rank holds the whole asset, sorts and view-calcs it redundantly, and composites only its own
-bands of 64-pixel bin rows (interleaved round-robin for load balance).  Each rank renders straight
-into its slice of the all-gather buffer ("band-packed": own bin row k -> pixel rows [64k,64k+64)),
-ONE all-gather moves the bands, and gs_unshuffle_bands assembles the image.  torch.distributed is
-plumbing only (process group + the collective); the partition arithmetic below is mirrored by the
-device code in csrc/gs_raster.cu (struct Partition) and tested against it.
+Two schemes live here, the second only as the baseline the first is measured against:
+
+* GaussianSplatGroup (below, second half) -- the product path: gs_group_* of the C ABI.  The depth sort is sharded by key range,
+  view-calc / binning / compositing by contiguous ranges of 16-pixel rows, the exchanges (NVLink peer stores or NCCL) are
+  made by the library itself; order and pixels are bit-identical to one GPU.  Python only holds the handles.
+* BandPartition / render_partitioned (first half) -- round 1's scheme: every rank sorts and view-calcs the whole asset
+  redundantly and composites only its own interleaved bands of 64-pixel bin rows, band-packed into its slice of an
+  all-gather buffer; ONE torch.distributed all-gather moves the bands and gs_unshuffle_bands assembles the image.  The
+  partition arithmetic is mirrored by the device code in csrc/gs_raster.cu (struct Partition) and tested against it.
 """
 from __future__ import annotations
 
@@ -109,7 +112,8 @@ def unshuffle(context, gathered, part: BandPartition, out_image):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # The group path (include/gsplat_b200.h "several GPUs"): key-range-sharded sort + row-range-sharded view-calc / binning /
-# compositing, both exchanges NCCL calls made by the library on its own stream.  Python only holds the handles.
+# compositing; the exchanges (peer stores over NVLink, or NCCL) are made by the library on its own streams.  Python only holds
+# the handles.
 # ---------------------------------------------------------------------------------------------------------------------
 def group_unique_id() -> bytes:
     """Rank 0 creates the id; every other process needs the same 128 bytes (send them over any host channel)."""
