@@ -43,7 +43,7 @@ def num(x):
 def main():
     report = sys.argv[1]
     print("# source-level hot spots of `%s`\n" % report.split("/")[-1])
-    print("`ncu --page source --print-source cuda,sass` of the committed capture, aggregated per source line (first launch of each kernel;")
+    print("`ncu --page source --print-source cuda,sass` of the capture summarised in `r02_ncu_summary.md` (the 33 MB report itself stays in scratch), aggregated per source line (first launch of each kernel;")
     print("stall samples are the sampler's, share = of the kernel's samples; warp-instr = `Instructions Executed`).  Line numbers are")
     print("those of the sources embedded in the capture (`--import-source on`), which later edits may have shifted by a few lines.\n")
     for title, kern in KERNELS:
